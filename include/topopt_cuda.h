@@ -1,0 +1,216 @@
+/*
+ * libtopopt_cuda -- C ABI of the B200 (sm_100a) SIMP inner loop behind TopOpt.jl's solver API.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, and is what the Julia
+ * glue binds with `ccall`.  Reference citations are file:line in
+ * JuliaTopOpt/TopOpt.jl v0.14.0.
+ *
+ * Conventions
+ *  - All vectors crossing the ABI are fp64 in the REFERENCE's ordering: dof vectors in Ferrite
+ *    DOF order (length ndof), element vectors in Ferrite cell order (length nel).  Indices
+ *    crossing the ABI (prescribed dofs, cell_dofs, CSC pattern) are 1-based Int64 like Julia's.
+ *  - A pointer may be host memory (pageable or pinned) or device memory of the handle's GPU;
+ *    copies use cudaMemcpyDefault.  A NULL *input* means "use the device-resident value from
+ *    the previous call"; a NULL *output* means "leave the result resident on the device".
+ *  - Return value: TOPOPT_OK (0) or a negative topopt_status; the message is available from
+ *    topopt_last_error().  CG non-convergence is NOT an error (the reference is silent:
+ *    src/FEA/solvers_api.jl:203); it is reported in topopt_cg_result.
+ *  - One handle = one caller thread at a time (the reference is single-task and mutates the
+ *    solver in place: src/Functions/compliance.jl:65-66).  Calls are synchronous on return.
+ *  - Multi-GPU: one process per GPU (rank), structured grid split into slabs along the last
+ *    axis; every rank passes the same full-length arrays and receives full-length results.
+ */
+#ifndef TOPOPT_CUDA_H
+#define TOPOPT_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct topopt_handle topopt_handle;
+typedef struct topopt_filter topopt_filter;
+
+typedef enum {
+  TOPOPT_OK = 0,
+  TOPOPT_ERR_INVALID = -1,    /* ArgumentError on the Julia side */
+  TOPOPT_ERR_CUDA = -2,
+  TOPOPT_ERR_NCCL = -3,
+  TOPOPT_ERR_NONFINITE = -4,  /* DomainError (src/FEA/convergence_criteria.jl:34-41) */
+  TOPOPT_ERR_NO_DEVICE = -5,
+  TOPOPT_ERR_MISMATCH = -6    /* caller's cell_dofs disagree with the internal numbering */
+} topopt_status;
+
+/* penalty kinds: src/Utilities/penalties.jl:30-54 */
+enum { TOPOPT_PENALTY_POWER = 0, TOPOPT_PENALTY_RATIONAL = 1, TOPOPT_PENALTY_SINH = 2 };
+/* operator used by topopt_solve: CGMatrixFreeSolver / CGAssemblySolver (solvers_api.jl:58,66) */
+enum { TOPOPT_OP_MATRIX_FREE = 0, TOPOPT_OP_ASSEMBLED = 1 };
+/* preconditioner: identity or DiagonalPreconditioner (Preconditioners.jl, solvers_api.jl:187-192) */
+enum { TOPOPT_PRECOND_NONE = 0, TOPOPT_PRECOND_JACOBI = 1 };
+/* convergence criteria: src/FEA/convergence_criteria.jl:13-45 */
+enum { TOPOPT_CRITERIA_DEFAULT = 0, TOPOPT_CRITERIA_ENERGY = 1 };
+/* physics for topopt_element_matrix */
+enum { TOPOPT_PHYSICS_ELASTICITY = 0, TOPOPT_PHYSICS_HEAT = 1 };
+/* filter application modes */
+enum {
+  TOPOPT_FILTER_FORWARD = 0,   /* J x          DensityFilterFun call, density_filter.jl:35-40;
+                                  also the SensFilterFun pullback map, sens_filter.jl:52-70     */
+  TOPOPT_FILTER_TRANSPOSE = 1  /* J' d         DensityFilterFun rrule, density_filter.jl:41-47 */
+};
+
+/* Problem description.  Replaces what GenericFEASolver holds on the CPU
+ * (src/FEA/solvers_api.jl:86-123): elementinfo.Kes[1], metadata.cell_dofs,
+ * ch.prescribed_dofs, elementinfo.fixedload, elementinfo.cellvolumes, meandiag. */
+typedef struct {
+  int32_t dim;                    /* 2 (quad4) or 3 (hex8)                                      */
+  int32_t ncomp;                  /* dofs per node: dim (elasticity) or 1 (heat)                 */
+  int64_t nels[3];                /* elements per axis (nels[2] ignored when dim == 2)           */
+  double sizes[3];                /* element edge lengths (filter geometry, cell volumes)        */
+  const double* Ke;               /* Kesize x Kesize, column-major like SMatrix; Kesize=ncomp*2^dim */
+  const int64_t* prescribed_dofs; /* 1-based Ferrite dofs (ch.prescribed_dofs), any order        */
+  int64_t n_prescribed;
+  const double* fixedload;        /* ndof, Ferrite order (elementinfo.fixedload); may be NULL=0  */
+  const double* cellvolumes;      /* nel or NULL (= prod(sizes)); must be uniform                */
+  const int64_t* cell_dofs;       /* optional Kesize x nel 1-based cross-check of the numbering  */
+  double fixed_diag;              /* y[d] = fixed_diag*x[d] on prescribed rows; <=0 selects the
+                                     reference's sum_e tr(Ke) (solvers_api.jl:526-527)           */
+  int32_t device;                 /* CUDA device ordinal                                         */
+  int32_t rank;                   /* slab rank in [0, world)                                     */
+  int32_t world;                  /* number of ranks (1 = single GPU)                            */
+  const void* nccl_unique_id;     /* 128-byte ncclUniqueId shared by all ranks (world > 1)       */
+} topopt_desc;
+
+typedef struct {
+  double abstol;          /* solver.abstol (default 1e-7, solvers_api.jl:489)                    */
+  double reltol;          /* IterativeSolvers default sqrt(eps); tol = max(reltol*|r0|, abstol)  */
+  int32_t maxiter;        /* solver.cg_max_iter (default 700, solvers_api.jl:478)                */
+  int32_t op;             /* TOPOPT_OP_*                                                         */
+  int32_t precond;        /* TOPOPT_PRECOND_*                                                    */
+  int32_t criteria;       /* TOPOPT_CRITERIA_*                                                   */
+  int32_t check_every;    /* host polls the device convergence flag every N iterations (0=auto) */
+  int32_t reserved;
+} topopt_cg_opts;
+
+typedef struct {
+  int32_t iters;
+  int32_t converged;
+  double residual;        /* final ||r||_2                                                       */
+  double tol;             /* tolerance that was applied                                          */
+  double solve_ms;        /* device time of the CG loop (CUDA events)                            */
+} topopt_cg_result;
+
+typedef struct {
+  int64_t ndof, nel, nnodes, nnz;
+  int64_t ndof_local, nel_local;  /* owned by this rank                                          */
+  int64_t kernel_launches;        /* launches of this library's kernels since create/reset       */
+  int64_t cg_iterations;          /* total CG iterations since create/reset                      */
+  int64_t h2d_bytes, d2h_bytes;   /* bytes copied through the ABI since create/reset             */
+  double last_apply_ms, last_solve_ms, last_sens_ms, last_filter_ms;
+} topopt_stats;
+
+/* ---- library / host-only helpers (no GPU needed) -------------------------------------- */
+const char* topopt_version(void);
+/* message of the last failing call on this thread (h may be NULL) */
+const char* topopt_last_error(const topopt_handle* h);
+
+/* sizes of the structured problem */
+int topopt_sizes(int32_t dim, int32_t ncomp, const int64_t* nels, int64_t* nnodes, int64_t* nel,
+                 int64_t* ndof, int64_t* nnz);
+/* Ferrite DofHandler numbering (src/TopOptProblems/metadata.jl:116-145): ncomp x nnodes, 1-based */
+int topopt_node_dofs(int32_t dim, int32_t ncomp, const int64_t* nels, int64_t* node_dofs);
+/* metadata.cell_dofs (metadata.jl:40-50): Kesize x nel column-major, 1-based */
+int topopt_cell_dofs(int32_t dim, int32_t ncomp, const int64_t* nels, int64_t* cell_dofs);
+/* grid.cells connectivity (Ferrite generate_grid): 2^dim x nel column-major, 1-based node ids */
+int topopt_cells(int32_t dim, const int64_t* nels, int64_t* cells);
+/* sparsity of allocate_matrix(dh) (src/TopOptProblems/matrices_and_vectors.jl:57):
+ * CSC colptr (ndof+1) and rowval (nnz), 1-based, rows sorted; symmetric so also valid CSR */
+int topopt_csc_pattern(int32_t dim, int32_t ncomp, const int64_t* nels, int64_t* colptr,
+                       int64_t* rowval);
+/* element matrix by Gauss quadrature (matrices_and_vectors.jl:63-177 elasticity, plane strain
+ * in 2-D; :413-496 heat).  a = E (elasticity) or k (heat); b = nu (elasticity).  Column-major. */
+int topopt_element_matrix(int32_t dim, int32_t physics, const double* sizes, double a, double b,
+                          int32_t quad_order, double* Ke);
+
+/* ncclGetUniqueId into a 128-byte buffer; rank 0 calls it and ships the bytes to the other
+ * ranks (any transport), every rank then passes them in topopt_desc.nccl_unique_id. */
+int topopt_nccl_unique_id(void* out128);
+
+/* ---- handle --------------------------------------------------------------------------- */
+/* FEASolver(Solver, problem; ...) (src/FEA/solvers_api.jl:468-574, 599-603) */
+int topopt_create(const topopt_desc* desc, topopt_handle** out);
+int topopt_destroy(topopt_handle* h);
+int topopt_get_stats(topopt_handle* h, topopt_stats* out);
+int topopt_reset_stats(topopt_handle* h);
+
+/* solver.vars .= x; penalised stiffness E_e and dE_e
+ * (penalties.jl:113-130; density utils.jl:77).  order: 1 = penalty then interpolation (default
+ * preference, LocalPreferences.toml:2), 0 = interpolation then penalty. */
+int topopt_set_density(topopt_handle* h, const double* rho, int32_t penalty_kind, double p,
+                       double xmin, int32_t penalty_before_interpolation);
+/* direct control of E_e / dE_e (nel each; dE may be NULL) */
+int topopt_set_stiffness(topopt_handle* h, const double* E, const double* dE);
+/* read back E_e, dE_e (nel each; either may be NULL) */
+int topopt_get_stiffness(topopt_handle* h, double* E, double* dE);
+
+/* mul!(y, MatrixFreeOperator, x)  (src/FEA/matrix_free_operator.jl:66-105) */
+int topopt_apply(topopt_handle* h, const double* x, double* y);
+
+/* assemble!(globalinfo, ...) + apply!  (src/TopOptProblems/assemble.jl:28-90).  nzval (nnz, in
+ * the order of topopt_csc_pattern) and f (ndof) may be NULL. */
+int topopt_assemble(topopt_handle* h, double* nzval, double* f);
+/* mul!(y, MatrixOperator, x)  (src/FEA/matrix_free_operator.jl:16) on the assembled matrix */
+int topopt_spmv(topopt_handle* h, const double* x, double* y);
+
+/* Jacobi preconditioner: diag = NULL computes diag K(rho) from the current stiffness
+ * (UpdatePreconditioner!, solvers_api.jl:187-192), else uploads the caller's diagonal. */
+int topopt_set_jacobi(topopt_handle* h, const double* diag);
+
+/* solver() : cg_solve! with zero initial guess (solvers_api.jl:177-282, IterativeSolvers cg!).
+ * rhs NULL = fixedload with prescribed entries zeroed (assemble.jl:51,87); a caller rhs gets
+ * apply_zero! (solvers_api.jl:364-367).  u may be NULL (stays resident for topopt_compliance). */
+int topopt_solve(topopt_handle* h, const double* rhs, double* u, const topopt_cg_opts* opts,
+                 topopt_cg_result* result);
+
+/* ComplianceFun call (src/Functions/compliance.jl:58-70, compute_element_energy.jl:18-38):
+ * cell_comp_e = u_e' Ke u_e, grad_e = -dE_e cell_comp_e, obj = sum E_e cell_comp_e. */
+int topopt_compliance(topopt_handle* h, const double* u, double* obj, double* cell_comp,
+                      double* grad);
+/* thermal/adjoint form (src/Functions/thermal_compliance.jl:144-155):
+ * cell_e = lambda_e' Ke u_e, grad_e = dE_e cell_e. */
+int topopt_bilinear_sens(topopt_handle* h, const double* lambda, const double* u,
+                         double* cell_out, double* grad);
+/* swap the device-resident solution with the device-resident lambda vector, so that a forward
+ * solve, a swap and an adjoint solve (solve_adjoint!, thermal_compliance.jl:169-210) leave both
+ * fields resident for topopt_bilinear_sens(h, NULL, NULL, ...). */
+int topopt_swap_solution_lambda(topopt_handle* h);
+/* dot(a, b) over dofs on the device (thermal J = dot(fixedload, u), thermal_compliance.jl:127;
+ * getcompliance).  a NULL = fixedload, b NULL = resident u. */
+int topopt_dot(topopt_handle* h, const double* a, const double* b, double* out);
+
+/* ---- filters (src/CheqFilters) -------------------------------------------------------- */
+/* FilterMetadata + getJacobian (CheqFilters.jl:66-118, density_filter.jl:49-108) without
+ * materialising J: two-stage cell->node->cell stencil with the reference's duplicate weights. */
+int topopt_filter_create(topopt_handle* h, double rmin, topopt_filter** out);
+int topopt_filter_apply(topopt_filter* f, const double* x, double* y, int32_t mode);
+int topopt_filter_destroy(topopt_filter* f);
+
+/* ---- fused device-resident SIMP evaluation -------------------------------------------- */
+/* x (nel, design) -> filter -> penalise -> solve -> compliance + sensitivity -> filter pullback.
+ * filter_kind: 0 none, 1 density (forward J x, pullback J' g), 2 sensitivity (identity forward,
+ * pullback J g).  x NULL = resident design.  grad_x (nel) may be NULL. */
+int topopt_simp_eval(topopt_handle* h, topopt_filter* f, int32_t filter_kind, const double* x,
+                     int32_t penalty_kind, double p, double xmin, const topopt_cg_opts* opts,
+                     double* obj, double* grad_x, topopt_cg_result* result);
+
+/* ---- measurement ---------------------------------------------------------------------- */
+/* time `reps` back-to-back launches of one kernel class with CUDA events on the library's
+ * stream; which: 0 = K.u matrix-free, 1 = CG iteration (matrix-free), 2 = sensitivity,
+ * 3 = filter forward, 4 = SpMV, 5 = assembly, 6 = CG iteration (assembled).  ms = average per rep. */
+int topopt_time_kernel(topopt_handle* h, topopt_filter* f, int32_t which, int32_t reps,
+                       double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOPOPT_CUDA_H */

@@ -729,9 +729,9 @@ def oc_update(x, dc, dv, volfrac, move=0.2, eta=0.5, xlo=0.0):
     return xn
 
 
-def simp_loop(prob, rmin, volfrac, p=3.0, xmin=1e-3, iters=10, filt="density", abstol=1e-10, maxiter=20000, solver="matfree"):
+def simp_loop(prob, rmin, volfrac, p=3.0, xmin=1e-3, iters=10, filt="density", abstol=1e-10, maxiter=20000, solver="matfree", reltol=1e-14):
     """x -> filter -> solve -> compliance/sens -> filter pullback -> OC.  Returns (x, history)."""
-    F = DensityFilter(prob, rmin) if filt == "density" else SensFilter(prob, rmin)
+    F = {"density": DensityFilter, "sens": SensFilter}[filt](prob, rmin)
     x = np.full(prob.nel, volfrac)
     dv = prob.cellvolumes / prob.cellvolumes.sum()
     hist = []
@@ -740,9 +740,9 @@ def simp_loop(prob, rmin, volfrac, p=3.0, xmin=1e-3, iters=10, filt="density", a
         xf = F(x)
         E = get_rho(xf, p, xmin)
         if prob.physics == "heat":
-            obj, _, g, _, _ = thermal_compliance(prob, xf, p, xmin, abstol=abstol, maxiter=maxiter)
+            obj, _, g, _, _ = thermal_compliance(prob, xf, p, xmin, abstol=abstol, maxiter=maxiter, reltol=reltol)
         else:
-            u, _, _ = solve(prob, E, abstol=abstol, maxiter=maxiter)
+            u, _, _ = solve(prob, E, abstol=abstol, maxiter=maxiter, reltol=reltol)
             obj, _, g = compliance(prob, u, xf, p, xmin)
         dc = F.pullback(g)
         dvf = F.pullback(dv) if filt == "density" else dv

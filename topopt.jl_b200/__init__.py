@@ -1,0 +1,23 @@
+"""topopt_jl_b200 -- host-side mirror of TopOpt.jl's SIMP inner-loop interface over
+libtopopt_cuda (hand-written fp64 CUDA for sm_100a).  See DESIGN.md / INTEGRATION.md."""
+from . import _lib
+from .cheqfilters import DensityFilterFun, SensFilterFun
+from .fea import (
+    AbstractLinearSolver,
+    CUDAAssemblySolver,
+    CUDAMatrixFreeSolver,
+    DefaultCriteria,
+    EnergyCriteria,
+    FEASolver,
+    GenericFEASolver,
+    PowerPenaltyFun,
+    PseudoDensities,
+    RationalPenaltyFun,
+    SinhPenaltyFun,
+    getcompliance,
+)
+from .functions import ComplianceFun, ThermalComplianceFun, VolumeFun
+from .problems import HalfMBB, HeatConductionProblem, HeatTree, Metadata, PointLoadCantilever, element_matrix
+from .simp import oc_update, simp_eval, simp_loop
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,0 +1,1184 @@
+// C ABI of libtopopt_cuda (see include/topopt_cuda.h).  Host orchestration of the kernels in
+// kernels.cuh: handle lifetime, layout conversion at the ABI edge, the CG loop, the slab halo
+// exchange and reductions over NCCL.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <mutex>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "kernels.cuh"
+
+using namespace topopt;
+
+// ---- NCCL, loaded lazily so that the library also loads where NCCL is absent -----------------
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load(std::string& err) {
+    if (lib) return true;
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) {
+      err = std::string("cannot load libnccl.so.2: ") + dlerror();
+      return false;
+    }
+#define TOPOPT_SYM(name) \
+  name = reinterpret_cast<decltype(name)>(dlsym(lib, "nccl" #name)); \
+  if (!name) { err = "libnccl lacks nccl" #name; return false; }
+    TOPOPT_SYM(GetUniqueId)
+    TOPOPT_SYM(CommInitRank)
+    TOPOPT_SYM(CommDestroy)
+    TOPOPT_SYM(AllReduce)
+    TOPOPT_SYM(Send)
+    TOPOPT_SYM(Recv)
+    TOPOPT_SYM(GroupStart)
+    TOPOPT_SYM(GroupEnd)
+    TOPOPT_SYM(GetErrorString)
+#undef TOPOPT_SYM
+    return true;
+  }
+};
+NcclApi g_nccl;
+}  // namespace
+
+struct topopt_handle {
+  uint64_t id = 0;
+  int dim = 0, nc = 0, ks = 0;
+  GridDims gd{};
+  Geo g{};
+  int device = 0, rank = 0, world = 1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  ncclComm_t comm = nullptr;
+  int64_t ndof = 0, nel = 0, nnodes = 0, nnz = 0;
+  int64_t nloc_nodes = 0, nloc_dofs = 0, off = 0, nown_dofs = 0;  // dof vectors
+  int64_t nloc_el = 0, eoff = 0, nown_el = 0;                     // element vectors
+  int64_t plane_dofs = 0;
+  double Ke[kMaxKe * kMaxKe];
+  double fixed_diag = 0.0, cellvol = 1.0;
+  double sizes[3] = {1, 1, 1};
+  // device buffers
+  int* d_block = nullptr;
+  unsigned char* d_fixed = nullptr;
+  double *d_b = nullptr, *d_fload = nullptr, *d_u = nullptr, *d_r = nullptr, *d_p = nullptr, *d_Ap = nullptr;
+  double *d_D = nullptr, *d_rhs = nullptr, *d_lam = nullptr, *d_tmp = nullptr;
+  double *d_E = nullptr, *d_dE = nullptr, *d_rho = nullptr, *d_cell = nullptr, *d_grad = nullptr;
+  double *d_full_dof = nullptr, *d_full_el = nullptr, *d_design = nullptr, *d_xf = nullptr, *d_gfull = nullptr;
+  double* d_partials = nullptr;
+  CGState* d_st = nullptr;
+  CGState* h_st = nullptr;  // pinned
+  bool have_jacobi = false;
+  // assembled path
+  long long* d_nbr_start = nullptr;
+  int* d_rowptr = nullptr;
+  int* d_col = nullptr;
+  double* d_nz = nullptr;
+  double* d_fasm = nullptr;
+  bool pattern_ready = false, assembled = false, stiffness_dirty = true;
+  std::vector<int64_t> export_map;  // CSC position (topopt_csc_pattern order) -> internal CSR position
+  std::vector<int64_t> node_of_block, block_of_node;
+  topopt_stats stats{};
+  std::string err;
+};
+
+struct topopt_filter {
+  topopt_handle* h = nullptr;
+  FilterGeo fg{};
+  double rmin = 0;
+  double* d_w = nullptr;
+  double* d_den = nullptr;
+  double* d_nodal = nullptr;
+  double* d_in = nullptr;
+  double* d_out = nullptr;
+};
+
+namespace {
+
+int fail(topopt_handle* h, int code, const std::string& msg) {
+  set_error(msg);
+  if (h) h->err = msg;
+  return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                          \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(h, TOPOPT_ERR_CUDA, std::string(#expr ": ") + cudaGetErrorString(e_));           \
+  } while (0)
+
+#define NCCL_TRY(h, expr)                                                                          \
+  do {                                                                                             \
+    ncclResult_t r_ = (expr);                                                                      \
+    if (r_ != ncclSuccess)                                                                         \
+      return fail(h, TOPOPT_ERR_NCCL, std::string(#expr ": ") + g_nccl.GetErrorString(r_));        \
+  } while (0)
+
+#define TRY(expr)                 \
+  do {                            \
+    int rc_ = (expr);             \
+    if (rc_ != TOPOPT_OK) return rc_; \
+  } while (0)
+
+#define DISPATCH(h, CALL)                    \
+  do {                                       \
+    if ((h)->dim == 2 && (h)->nc == 2) {     \
+      CALL(2, 2);                            \
+    } else if ((h)->dim == 2) {              \
+      CALL(2, 1);                            \
+    } else if ((h)->nc == 3) {               \
+      CALL(3, 3);                            \
+    } else {                                 \
+      CALL(3, 1);                            \
+    }                                        \
+  } while (0)
+
+inline int grid_for(long long n, int cap = kReduceBlocks) {
+  long long b = (n + kBlock - 1) / kBlock;
+  if (b < 1) b = 1;
+  return (int)std::min<long long>(b, cap);
+}
+constexpr int kWideGrid = 148 * 16;
+
+#define LAUNCH(h, kernel, grid, ...)                              \
+  do {                                                            \
+    kernel<<<(grid), kBlock, 0, (h)->stream>>>(__VA_ARGS__);      \
+    (h)->stats.kernel_launches += 1;                              \
+  } while (0)
+
+int check_launch(topopt_handle* h, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, TOPOPT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return TOPOPT_OK;
+}
+
+template <typename T>
+int dev_alloc(topopt_handle* h, T** p, size_t n) {
+  CUDA_TRY(h, cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+  CUDA_TRY(h, cudaMemsetAsync(*p, 0, std::max<size_t>(n, 1) * sizeof(T), h->stream));
+  return TOPOPT_OK;
+}
+
+// The shared element matrix lives in __constant__ memory (one copy per device).  Handles that
+// share a device re-upload it when ownership changes; such handles must not run concurrently.
+std::mutex g_const_mutex;
+uint64_t g_const_owner[64] = {0};
+std::atomic<uint64_t> g_next_id{1};
+
+int use_device(topopt_handle* h) {
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  std::lock_guard<std::mutex> lock(g_const_mutex);
+  if (g_const_owner[h->device & 63] != h->id) {
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    CUDA_TRY(h, cudaMemcpyToSymbol(cKe, h->Ke, sizeof(double) * h->ks * h->ks, 0, cudaMemcpyHostToDevice));
+    g_const_owner[h->device & 63] = h->id;
+  }
+  return TOPOPT_OK;
+}
+
+// ---- collectives ----------------------------------------------------------------------------
+int allreduce_sums(topopt_handle* h, int n) {
+  if (h->world == 1) return TOPOPT_OK;
+  NCCL_TRY(h, g_nccl.AllReduce(h->d_st->sums, h->d_st->gsums, n, ncclDouble, ncclSum, h->comm, h->stream));
+  return TOPOPT_OK;
+}
+
+// one node plane to each slab neighbour (ghost planes 0 and nown+1)
+int exchange_halo(topopt_handle* h, double* v) {
+  if (h->world == 1) return TOPOPT_OK;
+  const size_t ps = (size_t)h->plane_dofs;
+  NCCL_TRY(h, g_nccl.GroupStart());
+  if (h->rank + 1 < h->world) {
+    NCCL_TRY(h, g_nccl.Send(v + ps * h->g.nown, ps, ncclDouble, h->rank + 1, h->comm, h->stream));
+    NCCL_TRY(h, g_nccl.Recv(v + ps * (h->g.nown + 1), ps, ncclDouble, h->rank + 1, h->comm, h->stream));
+  }
+  if (h->rank > 0) {
+    NCCL_TRY(h, g_nccl.Send(v + ps, ps, ncclDouble, h->rank - 1, h->comm, h->stream));
+    NCCL_TRY(h, g_nccl.Recv(v, ps, ncclDouble, h->rank - 1, h->comm, h->stream));
+  }
+  NCCL_TRY(h, g_nccl.GroupEnd());
+  return TOPOPT_OK;
+}
+
+// ---- ABI edge: Ferrite-ordered full vectors <-> local slabs -----------------------------------
+int upload_dofs(topopt_handle* h, const double* src, double* dst_local) {
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_full_dof, src, sizeof(double) * h->ndof, cudaMemcpyDefault, h->stream));
+  h->stats.h2d_bytes += sizeof(double) * h->ndof;
+#define CALL(D, C) LAUNCH(h, (k_gather_dofs<C>), grid_for(h->nloc_nodes, kWideGrid), h->g, h->d_block, h->d_full_dof, dst_local)
+  DISPATCH(h, CALL);
+#undef CALL
+  return check_launch(h, "k_gather_dofs");
+}
+
+int download_dofs(topopt_handle* h, const double* src_local, double* dst) {
+  if (h->world > 1) CUDA_TRY(h, cudaMemsetAsync(h->d_full_dof, 0, sizeof(double) * h->ndof, h->stream));
+#define CALL(D, C) LAUNCH(h, (k_scatter_dofs<C>), grid_for(h->nloc_nodes, kWideGrid), h->g, h->d_block, src_local, h->d_full_dof)
+  DISPATCH(h, CALL);
+#undef CALL
+  TRY(check_launch(h, "k_scatter_dofs"));
+  if (h->world > 1)
+    NCCL_TRY(h, g_nccl.AllReduce(h->d_full_dof, h->d_full_dof, h->ndof, ncclDouble, ncclSum, h->comm, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(dst, h->d_full_dof, sizeof(double) * h->ndof, cudaMemcpyDefault, h->stream));
+  h->stats.d2h_bytes += sizeof(double) * h->ndof;
+  return TOPOPT_OK;
+}
+
+// element vectors: Ferrite cell order == lexicographic order, so a slab is a contiguous range
+int upload_elems(topopt_handle* h, const double* src_full, double* dst_local, bool count = true) {
+  const Geo& g = h->g;
+  const long long lo = std::max(g.p0, 0), hi = std::min<long long>(g.p0 + g.nown + 1, g.NLg);  // global layers
+  if (hi > lo) {
+    CUDA_TRY(h, cudaMemcpyAsync(dst_local + (lo - g.p0) * g.SE, src_full + lo * g.SE,
+                                sizeof(double) * (hi - lo) * g.SE, cudaMemcpyDefault, h->stream));
+    if (count) h->stats.h2d_bytes += sizeof(double) * (hi - lo) * g.SE;
+  }
+  return TOPOPT_OK;
+}
+
+// owned layers of a local element vector -> full vector at dst_dev_or_host
+int gather_elems_device(topopt_handle* h, const double* src_local, double** full_out) {
+  if (h->world == 1) {
+    *full_out = const_cast<double*>(src_local) + h->eoff;
+    return TOPOPT_OK;
+  }
+  const Geo& g = h->g;
+  CUDA_TRY(h, cudaMemsetAsync(h->d_full_el, 0, sizeof(double) * h->nel, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_full_el + (long long)(g.p0 + 1) * g.SE, src_local + h->eoff,
+                              sizeof(double) * h->nown_el, cudaMemcpyDeviceToDevice, h->stream));
+  NCCL_TRY(h, g_nccl.AllReduce(h->d_full_el, h->d_full_el, h->nel, ncclDouble, ncclSum, h->comm, h->stream));
+  *full_out = h->d_full_el;
+  return TOPOPT_OK;
+}
+
+int download_elems(topopt_handle* h, const double* src_local, double* dst) {
+  double* full = nullptr;
+  TRY(gather_elems_device(h, src_local, &full));
+  CUDA_TRY(h, cudaMemcpyAsync(dst, full, sizeof(double) * h->nel, cudaMemcpyDefault, h->stream));
+  h->stats.d2h_bytes += sizeof(double) * h->nel;
+  return TOPOPT_OK;
+}
+
+int sync(topopt_handle* h) {
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return TOPOPT_OK;
+}
+
+// ---- operator application -----------------------------------------------------------------
+template <bool DOT>
+int launch_apply(topopt_handle* h, const double* x, double* y, int fin) {
+  const int grid = DOT ? kReduceBlocks : grid_for((long long)h->g.S * h->g.nown, kWideGrid);
+#define CALL(D, C) \
+  LAUNCH(h, (k_apply<D, C, DOT>), grid, h->g, x, y, h->d_E, h->d_fixed, h->fixed_diag, h->d_partials, h->d_st, fin)
+  DISPATCH(h, CALL);
+#undef CALL
+  return check_launch(h, "k_apply");
+}
+
+template <bool DOT>
+int launch_spmv(topopt_handle* h, const double* x, double* y, int fin) {
+  const long long nrows = h->ndof;
+  const int lanes = (h->dim == 3 && h->nc == 3) ? 32 : 8;
+  const int grid = DOT ? kReduceBlocks : grid_for(nrows * lanes, kWideGrid);
+  if (lanes == 32)
+    LAUNCH(h, (k_spmv<32, DOT>), grid, nrows, h->d_rowptr, h->d_col, h->d_nz, x + h->off, y + h->off, h->d_partials,
+           h->d_st, fin);
+  else
+    LAUNCH(h, (k_spmv<8, DOT>), grid, nrows, h->d_rowptr, h->d_col, h->d_nz, x + h->off, y + h->off, h->d_partials,
+           h->d_st, fin);
+  return check_launch(h, "k_spmv");
+}
+
+int build_pattern(topopt_handle* h);
+int do_assemble(topopt_handle* h);
+
+// IterativeSolvers cg! with x0 = 0: see cg_finalize() for the scalar recurrences.
+// b (local layout) must already be zero on prescribed dofs.
+int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_cg_result* res, bool ignore_convergence = false,
+             int fixed_iters = 0) {
+  const bool assembled = o->op == TOPOPT_OP_ASSEMBLED;
+  if (assembled) {
+    if (h->world > 1) return fail(h, TOPOPT_ERR_INVALID, "the assembled operator is single-GPU only");
+    if (!h->assembled || h->stiffness_dirty) TRY(do_assemble(h));
+  }
+  const bool pre = o->precond == TOPOPT_PRECOND_JACOBI;
+  if (pre && !h->have_jacobi) return fail(h, TOPOPT_ERR_INVALID, "Jacobi preconditioner requested but topopt_set_jacobi was not called");
+  const bool energy = o->criteria == TOPOPT_CRITERIA_ENERGY;
+  CGState& s = *h->h_st;
+  std::memset(&s, 0, sizeof(CGState));
+  s.abstol = ignore_convergence ? -1.0 : o->abstol;
+  s.reltol = ignore_convergence ? 0.0 : o->reltol;
+  s.maxiter = ignore_convergence ? fixed_iters : o->maxiter;
+  s.criteria = ignore_convergence ? 0 : o->criteria;
+  s.precond = pre ? 1 : 0;
+  s.world = h->world;
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_st, &s, sizeof(CGState), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+  const double* D = pre ? h->d_D : nullptr;
+  const int vgrid = kReduceBlocks;
+  LAUNCH(h, k_cg_init, vgrid, h->off, h->nown_dofs, b, h->d_u, h->d_r, h->d_p, D, h->d_partials, h->d_st);
+  TRY(check_launch(h, "k_cg_init"));
+  if (h->world > 1) {
+    TRY(allreduce_sums(h, 2));
+    k_finalize<<<1, 1, 0, h->stream>>>(h->d_st, FIN_INIT);
+    h->stats.kernel_launches += 1;
+  }
+  int batch = o->check_every > 0 ? o->check_every : (h->ndof > 2000000 ? 25 : 50);
+  int issued = 0;
+  const int maxiter = s.maxiter;
+  while (true) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_st, h->d_st, sizeof(CGState), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->h_st->done || issued >= maxiter) break;
+    const int n = std::min(batch, maxiter - issued);
+    for (int it = 0; it < n; ++it) {
+      LAUNCH(h, k_update_p, vgrid, h->off, h->nown_dofs, h->d_r, h->d_p, D, h->d_st);
+      if (assembled) {
+        TRY(launch_spmv<true>(h, h->d_p, h->d_Ap, FIN_PAP));
+      } else {
+        TRY(exchange_halo(h, h->d_p));
+        TRY(launch_apply<true>(h, h->d_p, h->d_Ap, FIN_PAP));
+      }
+      if (h->world > 1) {
+        TRY(allreduce_sums(h, 1));
+        k_finalize<<<1, 1, 0, h->stream>>>(h->d_st, FIN_PAP);
+        h->stats.kernel_launches += 1;
+      }
+      if (energy)
+        LAUNCH(h, (k_update_xr<true>), vgrid, h->off, h->nown_dofs, h->d_u, h->d_r, h->d_p, h->d_Ap, D, b,
+               h->d_partials, h->d_st);
+      else
+        LAUNCH(h, (k_update_xr<false>), vgrid, h->off, h->nown_dofs, h->d_u, h->d_r, h->d_p, h->d_Ap, D, b,
+               h->d_partials, h->d_st);
+      if (h->world > 1) {
+        TRY(allreduce_sums(h, 4));
+        k_finalize<<<1, 1, 0, h->stream>>>(h->d_st, FIN_RR);
+        h->stats.kernel_launches += 1;
+      }
+    }
+    TRY(check_launch(h, "cg iteration"));
+    issued += n;
+  }
+  CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+  // ghost planes of the solution are needed by the sensitivity kernel
+  TRY(exchange_halo(h, h->d_u));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->stats.cg_iterations += h->h_st->iters;
+  h->stats.last_solve_ms = ms;
+  if (res) {
+    res->iters = h->h_st->iters;
+    res->converged = h->h_st->converged;
+    res->residual = h->h_st->res;
+    res->tol = h->h_st->tol;
+    res->solve_ms = ms;
+  }
+  if (h->h_st->nonfinite)
+    return fail(h, TOPOPT_ERR_NONFINITE, "CG: NaN or negative energy detected (EnergyCriteria / residual)");
+  return TOPOPT_OK;
+}
+
+int run_sens(topopt_handle* h, const double* u, const double* v, double gsign, double* obj_out) {
+  CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+#define CALL(D, C) \
+  LAUNCH(h, (k_sens<D, C>), kReduceBlocks, h->g, u, v, h->d_E, h->d_dE, h->d_cell, h->d_grad, gsign, h->d_partials, h->d_st)
+  DISPATCH(h, CALL);
+#undef CALL
+  TRY(check_launch(h, "k_sens"));
+  if (h->world > 1)
+    NCCL_TRY(h, g_nccl.AllReduce(h->d_st->sums, h->d_st->sums, 1, ncclDouble, ncclSum, h->comm, h->stream));
+  CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_st, h->d_st, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->stats.last_sens_ms = ms;
+  if (obj_out) *obj_out = h->h_st->sums[0];
+  return TOPOPT_OK;
+}
+
+int penalize(topopt_handle* h, int kind, double p, double xmin, int pen_first) {
+  if (kind < 0 || kind > 2) return fail(h, TOPOPT_ERR_INVALID, "unknown penalty kind");
+  LAUNCH(h, k_penalize, grid_for(h->nloc_el, kWideGrid), (long long)h->nloc_el, h->d_rho, h->d_E, h->d_dE, kind, p, xmin,
+         pen_first);
+  h->stiffness_dirty = true;
+  return check_launch(h, "k_penalize");
+}
+
+// ---- filter internals ---------------------------------------------------------------------
+int filter_run(topopt_filter* f, const double* in_dev, double* out_dev, int mode) {
+  topopt_handle* h = f->h;
+  const long long nn = (long long)f->fg.NX * f->fg.NY * f->fg.NZ;
+  const long long ne = (long long)f->fg.nx * f->fg.ny * f->fg.nz;
+  if (mode == TOPOPT_FILTER_FORWARD) {
+    LAUNCH(h, k_filter_c2n, grid_for(nn, kWideGrid), f->fg, in_dev, f->d_nodal);
+    LAUNCH(h, (k_filter_n2c<0>), grid_for(ne, kWideGrid), f->fg, f->d_w, f->d_nodal, f->d_den, out_dev);
+  } else {
+    LAUNCH(h, k_filter_c2n_T, grid_for(nn, kWideGrid), f->fg, f->d_w, in_dev, f->d_den, f->d_nodal);
+    LAUNCH(h, k_filter_n2c_T, grid_for(ne, kWideGrid), f->fg, f->d_nodal, out_dev);
+  }
+  return check_launch(h, "filter");
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* topopt_last_error(const topopt_handle* h) {
+  if (h && !h->err.empty()) return h->err.c_str();
+  return g_last_error.c_str();
+}
+
+int topopt_nccl_unique_id(void* out128) {
+  if (!out128) return fail(nullptr, TOPOPT_ERR_INVALID, "topopt_nccl_unique_id: NULL argument");
+  std::string err;
+  if (!g_nccl.load(err)) return fail(nullptr, TOPOPT_ERR_NCCL, err);
+  ncclUniqueId id;
+  ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r != ncclSuccess) return fail(nullptr, TOPOPT_ERR_NCCL, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  std::memcpy(out128, &id, sizeof(id));
+  return TOPOPT_OK;
+}
+
+int topopt_create(const topopt_desc* d, topopt_handle** out) {
+  if (!d || !out) return fail(nullptr, TOPOPT_ERR_INVALID, "topopt_create: NULL argument");
+  *out = nullptr;
+  if (!check_dims(d->dim, d->ncomp, d->nels)) return TOPOPT_ERR_INVALID;
+  if (!d->Ke) return fail(nullptr, TOPOPT_ERR_INVALID, "topopt_create: Ke is NULL");
+  if (d->world < 1 || d->rank < 0 || d->rank >= d->world)
+    return fail(nullptr, TOPOPT_ERR_INVALID, "topopt_create: bad rank/world");
+  if (d->world > 1 && !d->nccl_unique_id)
+    return fail(nullptr, TOPOPT_ERR_INVALID, "topopt_create: world > 1 needs nccl_unique_id");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, TOPOPT_ERR_NO_DEVICE,
+                "topopt_create: no CUDA device available (libtopopt_cuda has no CPU fallback)");
+  }
+  if (d->device < 0 || d->device >= ndev) return fail(nullptr, TOPOPT_ERR_INVALID, "topopt_create: bad device ordinal");
+
+  topopt_handle* h = new topopt_handle();
+  h->id = g_next_id.fetch_add(1);
+  h->dim = d->dim;
+  h->nc = d->ncomp;
+  h->ks = (1 << d->dim) * d->ncomp;
+  h->gd = make_dims(d->dim, d->nels);
+  h->device = d->device;
+  h->rank = d->rank;
+  h->world = d->world;
+  const GridDims& gd = h->gd;
+  h->nnodes = gd.nnodes;
+  h->nel = gd.nel;
+  h->ndof = gd.nnodes * h->nc;
+  h->nnz = pattern_nnz(gd, h->nc);
+  if (h->ndof >= (int64_t(1) << 31)) {
+    delete h;
+    return fail(nullptr, TOPOPT_ERR_INVALID, "topopt_create: more than 2^31 dofs are not supported");
+  }
+  for (int a = 0; a < 3; ++a) h->sizes[a] = a < d->dim ? d->sizes[a] : 1.0;
+  for (int a = 0; a < d->dim; ++a)
+    if (!(h->sizes[a] > 0)) {
+      delete h;
+      return fail(nullptr, TOPOPT_ERR_INVALID, "topopt_create: sizes must be positive");
+    }
+  h->cellvol = 1.0;
+  for (int a = 0; a < d->dim; ++a) h->cellvol *= h->sizes[a];
+  if (d->cellvolumes) {
+    for (int64_t e = 0; e < h->nel; ++e)
+      if (std::fabs(d->cellvolumes[e] - d->cellvolumes[0]) > 1e-12 * std::fabs(d->cellvolumes[0])) {
+        delete h;
+        return fail(nullptr, TOPOPT_ERR_INVALID, "topopt_create: non-uniform cellvolumes are not supported on the structured grid");
+      }
+    h->cellvol = d->cellvolumes[0];
+  }
+  std::memcpy(h->Ke, d->Ke, sizeof(double) * h->ks * h->ks);
+  for (int r = 0; r < h->ks; ++r)
+    for (int c = 0; c < h->ks; ++c)
+      if (!std::isfinite(h->Ke[r + h->ks * c])) {
+        delete h;
+        return fail(nullptr, TOPOPT_ERR_NONFINITE, "topopt_create: Ke has non-finite entries");
+      }
+  double tr = 0.0;
+  for (int r = 0; r < h->ks; ++r) tr += h->Ke[r * (h->ks + 1)];
+  h->fixed_diag = d->fixed_diag > 0 ? d->fixed_diag : tr * (double)h->nel;  // solvers_api.jl:526-527
+
+  // slab partition along the last axis
+  const int NLg = (int)(h->dim == 3 ? gd.nz : gd.ny);
+  const int NPg = NLg + 1;
+  if (NLg < h->world) {
+    delete h;
+    return fail(nullptr, TOPOPT_ERR_INVALID, "topopt_create: fewer element layers than ranks");
+  }
+  const int e0 = (int)((int64_t)h->rank * NLg / h->world), e1 = (int)((int64_t)(h->rank + 1) * NLg / h->world);
+  Geo& g = h->g;
+  g.NX = (int)gd.NX;
+  g.NY = h->dim == 3 ? (int)gd.NY : 1;
+  g.nx = (int)gd.nx;
+  g.ny = h->dim == 3 ? (int)gd.ny : 1;
+  g.S = g.NX * g.NY;
+  g.SE = g.nx * g.ny;
+  g.NPg = NPg;
+  g.NLg = NLg;
+  g.p0 = e0 - 1;
+  g.nlay = e1 - e0;
+  g.nown = (h->rank == h->world - 1) ? (NPg - e0) : (e1 - e0);
+  h->nloc_nodes = (int64_t)g.S * (g.nown + 2);
+  h->nloc_dofs = h->nloc_nodes * h->nc;
+  h->plane_dofs = (int64_t)g.S * h->nc;
+  h->off = h->plane_dofs;
+  h->nown_dofs = h->plane_dofs * g.nown;
+  h->nloc_el = (int64_t)g.SE * (g.nown + 1);
+  h->eoff = g.SE;
+  h->nown_el = (int64_t)g.SE * g.nlay;
+
+  // numbering
+  h->block_of_node = ferrite_node_blocks(gd);
+  h->node_of_block.resize(gd.nnodes);
+  for (int64_t n = 0; n < gd.nnodes; ++n) h->node_of_block[h->block_of_node[n]] = n;
+  if (d->cell_dofs) {
+    const int nen = 1 << h->dim;
+    int64_t nodes[8];
+    for (int64_t e = 0; e < gd.nel; ++e) {
+      cell_nodes(gd, e, nodes);
+      for (int a = 0; a < nen; ++a)
+        for (int c = 0; c < h->nc; ++c)
+          if (d->cell_dofs[e * h->ks + a * h->nc + c] != h->block_of_node[nodes[a]] * h->nc + c + 1) {
+            delete h;
+            return fail(nullptr, TOPOPT_ERR_MISMATCH,
+                        "topopt_create: caller's cell_dofs differ from the structured-grid Ferrite numbering");
+          }
+    }
+  }
+  std::vector<unsigned char> flags(gd.nnodes, 0);
+  for (int64_t k = 0; k < d->n_prescribed; ++k) {
+    const int64_t dof = d->prescribed_dofs[k] - 1;
+    if (dof < 0 || dof >= h->ndof) {
+      delete h;
+      return fail(nullptr, TOPOPT_ERR_INVALID, "topopt_create: prescribed dof out of range");
+    }
+    flags[h->node_of_block[dof / h->nc]] |= (unsigned char)(1u << (dof % h->nc));
+  }
+
+  auto bail = [&](int rc) {
+    topopt_destroy(h);
+    return rc;
+  };
+#define CTRY(expr)                         \
+  do {                                     \
+    int rc__ = (expr);                     \
+    if (rc__ != TOPOPT_OK) return bail(rc__); \
+  } while (0)
+#define CCUDA(expr)                                                                              \
+  do {                                                                                           \
+    cudaError_t e_ = (expr);                                                                     \
+    if (e_ != cudaSuccess) {                                                                     \
+      fail(nullptr, TOPOPT_ERR_CUDA, std::string(#expr ": ") + cudaGetErrorString(e_));          \
+      return bail(TOPOPT_ERR_CUDA);                                                              \
+    }                                                                                            \
+  } while (0)
+
+  CCUDA(cudaSetDevice(h->device));
+  CCUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CCUDA(cudaEventCreate(&h->ev0));
+  CCUDA(cudaEventCreate(&h->ev1));
+  CCUDA(cudaMallocHost((void**)&h->h_st, sizeof(CGState)));
+  CTRY(dev_alloc(h, &h->d_st, 1));
+  CTRY(dev_alloc(h, &h->d_partials, (size_t)kWideGrid * 4));
+  CTRY(dev_alloc(h, &h->d_block, h->nloc_nodes));
+  CTRY(dev_alloc(h, &h->d_fixed, h->nloc_nodes));
+  for (double** v : {&h->d_b, &h->d_fload, &h->d_u, &h->d_r, &h->d_p, &h->d_Ap, &h->d_D, &h->d_rhs, &h->d_lam, &h->d_tmp})
+    CTRY(dev_alloc(h, v, h->nloc_dofs));
+  for (double** v : {&h->d_E, &h->d_dE, &h->d_rho, &h->d_cell, &h->d_grad}) CTRY(dev_alloc(h, v, h->nloc_el));
+  CTRY(dev_alloc(h, &h->d_full_dof, h->ndof));
+  for (double** v : {&h->d_full_el, &h->d_design, &h->d_xf, &h->d_gfull}) CTRY(dev_alloc(h, v, h->nel));
+
+  {  // local numbering and flags
+    std::vector<int> lblock(h->nloc_nodes, 0);
+    std::vector<unsigned char> lfixed(h->nloc_nodes, 0);
+    for (int lp = 0; lp < g.nown + 2; ++lp) {
+      const int gp = lp + g.p0;
+      if (gp < 0 || gp >= NPg) continue;
+      for (int64_t q = 0; q < g.S; ++q) {
+        lblock[(int64_t)lp * g.S + q] = (int)h->block_of_node[(int64_t)gp * g.S + q];
+        lfixed[(int64_t)lp * g.S + q] = flags[(int64_t)gp * g.S + q];
+      }
+    }
+    CCUDA(cudaMemcpyAsync(h->d_block, lblock.data(), sizeof(int) * h->nloc_nodes, cudaMemcpyHostToDevice, h->stream));
+    CCUDA(cudaMemcpyAsync(h->d_fixed, lfixed.data(), h->nloc_nodes, cudaMemcpyHostToDevice, h->stream));
+    CCUDA(cudaStreamSynchronize(h->stream));
+  }
+  if (h->world > 1) {
+    std::string err;
+    if (!g_nccl.load(err)) {
+      fail(nullptr, TOPOPT_ERR_NCCL, err);
+      return bail(TOPOPT_ERR_NCCL);
+    }
+    ncclUniqueId id;
+    std::memcpy(&id, d->nccl_unique_id, sizeof(id));
+    ncclResult_t r = g_nccl.CommInitRank(&h->comm, h->world, id, h->rank);
+    if (r != ncclSuccess) {
+      fail(nullptr, TOPOPT_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+      return bail(TOPOPT_ERR_NCCL);
+    }
+  }
+  CTRY(use_device(h));
+  if (d->fixedload) {
+    CTRY(upload_dofs(h, d->fixedload, h->d_fload));
+    CCUDA(cudaMemcpyAsync(h->d_b, h->d_fload, sizeof(double) * h->nloc_dofs, cudaMemcpyDeviceToDevice, h->stream));
+#define CALL(D, C) LAUNCH(h, (k_apply_zero<C>), grid_for(h->nloc_nodes, kWideGrid), (long long)h->nloc_nodes, h->d_fixed, h->d_b)
+    DISPATCH(h, CALL);
+#undef CALL
+  }
+  // E = 1 until a density is set (solver.vars = ones, solvers_api.jl:501 with penalty p = 1)
+  {
+    std::vector<double> ones(h->nloc_el, 1.0);
+    CCUDA(cudaMemcpyAsync(h->d_rho, ones.data(), sizeof(double) * h->nloc_el, cudaMemcpyHostToDevice, h->stream));
+    CCUDA(cudaMemcpyAsync(h->d_E, ones.data(), sizeof(double) * h->nloc_el, cudaMemcpyHostToDevice, h->stream));
+    CCUDA(cudaMemcpyAsync(h->d_dE, ones.data(), sizeof(double) * h->nloc_el, cudaMemcpyHostToDevice, h->stream));
+    CCUDA(cudaStreamSynchronize(h->stream));
+  }
+  CTRY(check_launch(h, "topopt_create"));
+  CCUDA(cudaStreamSynchronize(h->stream));
+  std::memset(&h->stats, 0, sizeof(h->stats));
+#undef CTRY
+#undef CCUDA
+  *out = h;
+  return TOPOPT_OK;
+}
+
+int topopt_destroy(topopt_handle* h) {
+  if (!h) return TOPOPT_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  void* ptrs[] = {h->d_block, h->d_fixed, h->d_b, h->d_fload, h->d_u, h->d_r, h->d_p, h->d_Ap, h->d_D, h->d_rhs, h->d_lam,
+                  h->d_tmp, h->d_E, h->d_dE, h->d_rho, h->d_cell, h->d_grad, h->d_full_dof, h->d_full_el, h->d_design,
+                  h->d_xf, h->d_gfull, h->d_partials, h->d_st, h->d_nbr_start, h->d_rowptr, h->d_col, h->d_nz, h->d_fasm};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (h->h_st) cudaFreeHost(h->h_st);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return TOPOPT_OK;
+}
+
+int topopt_get_stats(topopt_handle* h, topopt_stats* out) {
+  if (!h || !out) return fail(h, TOPOPT_ERR_INVALID, "topopt_get_stats: NULL argument");
+  h->stats.ndof = h->ndof;
+  h->stats.nel = h->nel;
+  h->stats.nnodes = h->nnodes;
+  h->stats.nnz = h->nnz;
+  h->stats.ndof_local = h->nown_dofs;
+  h->stats.nel_local = h->nown_el;
+  *out = h->stats;
+  return TOPOPT_OK;
+}
+
+int topopt_reset_stats(topopt_handle* h) {
+  if (!h) return fail(h, TOPOPT_ERR_INVALID, "topopt_reset_stats: NULL handle");
+  std::memset(&h->stats, 0, sizeof(h->stats));
+  return TOPOPT_OK;
+}
+
+int topopt_set_density(topopt_handle* h, const double* rho, int32_t kind, double p, double xmin, int32_t pen_first) {
+  if (!h) return fail(h, TOPOPT_ERR_INVALID, "topopt_set_density: NULL handle");
+  TRY(use_device(h));
+  if (rho) TRY(upload_elems(h, rho, h->d_rho));
+  TRY(penalize(h, kind, p, xmin, pen_first));
+  return sync(h);
+}
+
+int topopt_set_stiffness(topopt_handle* h, const double* E, const double* dE) {
+  if (!h || !E) return fail(h, TOPOPT_ERR_INVALID, "topopt_set_stiffness: NULL argument");
+  TRY(use_device(h));
+  TRY(upload_elems(h, E, h->d_E));
+  if (dE) TRY(upload_elems(h, dE, h->d_dE));
+  h->stiffness_dirty = true;
+  return sync(h);
+}
+
+int topopt_get_stiffness(topopt_handle* h, double* E, double* dE) {
+  if (!h) return fail(h, TOPOPT_ERR_INVALID, "topopt_get_stiffness: NULL handle");
+  TRY(use_device(h));
+  if (E) TRY(download_elems(h, h->d_E, E));
+  if (E && dE) TRY(sync(h));
+  if (dE) TRY(download_elems(h, h->d_dE, dE));
+  return sync(h);
+}
+
+int topopt_apply(topopt_handle* h, const double* x, double* y) {
+  if (!h) return fail(h, TOPOPT_ERR_INVALID, "topopt_apply: NULL handle");
+  TRY(use_device(h));
+  if (x) TRY(upload_dofs(h, x, h->d_p));
+  CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+  TRY(launch_apply<false>(h, h->d_p, h->d_Ap, FIN_NONE));
+  CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+  if (y) TRY(download_dofs(h, h->d_Ap, y));
+  TRY(sync(h));
+  float ms = 0;
+  CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->stats.last_apply_ms = ms;
+  return TOPOPT_OK;
+}
+
+int topopt_set_jacobi(topopt_handle* h, const double* diag) {
+  if (!h) return fail(h, TOPOPT_ERR_INVALID, "topopt_set_jacobi: NULL handle");
+  TRY(use_device(h));
+  if (diag) {
+    TRY(upload_dofs(h, diag, h->d_D));
+  } else {
+#define CALL(D, C) LAUNCH(h, (k_diag<D, C>), grid_for((long long)h->g.S * h->g.nown, kWideGrid), h->g, h->d_D, h->d_E, h->d_fixed, h->fixed_diag)
+    DISPATCH(h, CALL);
+#undef CALL
+    TRY(check_launch(h, "k_diag"));
+  }
+  h->have_jacobi = true;
+  return sync(h);
+}
+
+int topopt_solve(topopt_handle* h, const double* rhs, double* u, const topopt_cg_opts* opts, topopt_cg_result* result) {
+  if (!h || !opts) return fail(h, TOPOPT_ERR_INVALID, "topopt_solve: NULL argument");
+  if (opts->maxiter < 0 || !(opts->abstol >= 0) || !(opts->reltol >= 0))
+    return fail(h, TOPOPT_ERR_INVALID, "topopt_solve: bad tolerances / maxiter");
+  TRY(use_device(h));
+  const double* b = h->d_b;
+  if (rhs) {
+    TRY(upload_dofs(h, rhs, h->d_rhs));
+#define CALL(D, C) LAUNCH(h, (k_apply_zero<C>), grid_for(h->nloc_nodes, kWideGrid), (long long)h->nloc_nodes, h->d_fixed, h->d_rhs)
+    DISPATCH(h, CALL);  // apply_zero!(rhs, ch), solvers_api.jl:364-367
+#undef CALL
+    b = h->d_rhs;
+  }
+  TRY(cg_solve(h, b, opts, result));
+  if (u) {
+    TRY(download_dofs(h, h->d_u, u));
+    TRY(sync(h));
+  }
+  return TOPOPT_OK;
+}
+
+int topopt_compliance(topopt_handle* h, const double* u, double* obj, double* cell_comp, double* grad) {
+  if (!h) return fail(h, TOPOPT_ERR_INVALID, "topopt_compliance: NULL handle");
+  TRY(use_device(h));
+  if (u) TRY(upload_dofs(h, u, h->d_u));
+  TRY(run_sens(h, h->d_u, h->d_u, -1.0, obj));
+  if (cell_comp) {
+    TRY(download_elems(h, h->d_cell, cell_comp));
+    TRY(sync(h));
+  }
+  if (grad) TRY(download_elems(h, h->d_grad, grad));
+  return sync(h);
+}
+
+int topopt_bilinear_sens(topopt_handle* h, const double* lambda, const double* u, double* cell_out, double* grad) {
+  if (!h) return fail(h, TOPOPT_ERR_INVALID, "topopt_bilinear_sens: NULL handle");
+  TRY(use_device(h));
+  if (u) TRY(upload_dofs(h, u, h->d_u));
+  if (lambda) TRY(upload_dofs(h, lambda, h->d_lam));
+  TRY(run_sens(h, h->d_u, h->d_lam, 1.0, nullptr));
+  if (cell_out) {
+    TRY(download_elems(h, h->d_cell, cell_out));
+    TRY(sync(h));
+  }
+  if (grad) TRY(download_elems(h, h->d_grad, grad));
+  return sync(h);
+}
+
+int topopt_dot(topopt_handle* h, const double* a, const double* b, double* out) {
+  if (!h || !out) return fail(h, TOPOPT_ERR_INVALID, "topopt_dot: NULL argument");
+  TRY(use_device(h));
+  const double* da = h->d_fload;
+  const double* db = h->d_u;
+  if (a) {
+    TRY(upload_dofs(h, a, h->d_tmp));
+    da = h->d_tmp;
+  }
+  if (b) {
+    TRY(upload_dofs(h, b, h->d_rhs));
+    db = h->d_rhs;
+  }
+  LAUNCH(h, k_dot, kReduceBlocks, h->off, h->nown_dofs, da, db, h->d_partials, h->d_st);
+  TRY(check_launch(h, "k_dot"));
+  if (h->world > 1)
+    NCCL_TRY(h, g_nccl.AllReduce(h->d_st->sums, h->d_st->sums, 1, ncclDouble, ncclSum, h->comm, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_st, h->d_st, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  TRY(sync(h));
+  *out = h->h_st->sums[0];
+  return TOPOPT_OK;
+}
+
+// swap the resident solution with the resident lambda vector: solve (T), swap, solve adjoint
+// (lambda), then topopt_bilinear_sens(h, NULL, NULL, ...) evaluates T_e' Ke lambda_e.
+int topopt_swap_solution_lambda(topopt_handle* h) {
+  if (!h) return fail(h, TOPOPT_ERR_INVALID, "topopt_swap_solution_lambda: NULL handle");
+  TRY(sync(h));
+  std::swap(h->d_u, h->d_lam);
+  return TOPOPT_OK;
+}
+
+// ---- assembled path ---------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+int build_pattern(topopt_handle* h) {
+  if (h->pattern_ready) return TOPOPT_OK;
+  if (h->world > 1) return fail(h, TOPOPT_ERR_INVALID, "the assembled operator is single-GPU only");
+  if (h->nnz >= (int64_t(1) << 31)) return fail(h, TOPOPT_ERR_INVALID, "assembled pattern exceeds 2^31 non-zeros; use the matrix-free operator");
+  const GridDims& gd = h->gd;
+  const int nc = h->nc;
+  std::vector<long long> nbr_start(gd.nnodes + 1, 0);
+  std::vector<int> rowptr(h->ndof + 1, 0);
+  for (int64_t n = 0; n < gd.nnodes; ++n) {
+    const int64_t i = n % gd.NX, j = (n / gd.NX) % gd.NY, k = n / (gd.NX * gd.NY);
+    const int cx = 1 + (i > 0) + (i < gd.NX - 1);
+    const int cy = 1 + (j > 0) + (j < gd.NY - 1);
+    const int cz = gd.dim == 3 ? 1 + (k > 0) + (k < gd.NZ - 1) : 1;
+    const int cnt = cx * cy * cz;
+    nbr_start[n + 1] = nbr_start[n] + cnt;
+    for (int c = 0; c < nc; ++c) rowptr[n * nc + c + 1] = (int)((long long)nc * nc * nbr_start[n] + (long long)(c + 1) * nc * cnt);
+  }
+  TRY(dev_alloc(h, &h->d_nbr_start, gd.nnodes + 1));
+  TRY(dev_alloc(h, &h->d_rowptr, h->ndof + 1));
+  TRY(dev_alloc(h, &h->d_col, h->nnz));
+  TRY(dev_alloc(h, &h->d_nz, h->nnz));
+  TRY(dev_alloc(h, &h->d_fasm, h->ndof));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_nbr_start, nbr_start.data(), sizeof(long long) * (gd.nnodes + 1), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_rowptr, rowptr.data(), sizeof(int) * (h->ndof + 1), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->pattern_ready = true;
+  return TOPOPT_OK;
+}
+
+// CSC position (Ferrite order, as topopt_csc_pattern emits it) -> internal CSR position
+void build_export_map(topopt_handle* h) {
+  if (!h->export_map.empty()) return;
+  const GridDims& gd = h->gd;
+  const int nc = h->nc;
+  h->export_map.resize(h->nnz);
+  std::vector<long long> nbr_start(gd.nnodes + 1, 0);
+  auto count = [&](int64_t n) {
+    const int64_t i = n % gd.NX, j = (n / gd.NX) % gd.NY, k = n / (gd.NX * gd.NY);
+    const int cx = 1 + (i > 0) + (i < gd.NX - 1);
+    const int cy = 1 + (j > 0) + (j < gd.NY - 1);
+    const int cz = gd.dim == 3 ? 1 + (k > 0) + (k < gd.NZ - 1) : 1;
+    return cx * cy * cz;
+  };
+  for (int64_t n = 0; n < gd.nnodes; ++n) nbr_start[n + 1] = nbr_start[n] + count(n);
+  struct Ent {
+    int64_t fdof;
+    int64_t pos;
+  };
+  std::vector<Ent> ents;
+  int64_t out = 0;
+  for (int64_t b = 0; b < gd.nnodes; ++b) {  // Ferrite column block
+    const int64_t m = h->node_of_block[b];   // column node (lexicographic)
+    const int64_t i = m % gd.NX, j = (m / gd.NX) % gd.NY, k = m / (gd.NX * gd.NY);
+    for (int c2 = 0; c2 < nc; ++c2) {
+      ents.clear();
+      // rows of column (m,c2): all neighbour nodes n of m and components c; K[(n,c),(m,c2)]
+      for (int64_t dk = (gd.dim == 3 ? -1 : 0); dk <= (gd.dim == 3 ? 1 : 0); ++dk)
+        for (int64_t dj = -1; dj <= 1; ++dj)
+          for (int64_t di = -1; di <= 1; ++di) {
+            const int64_t ii = i + di, jj = j + dj, kk = k + dk;
+            if (ii < 0 || ii >= gd.NX || jj < 0 || jj >= gd.NY || kk < 0 || kk >= gd.NZ) continue;
+            const int64_t n = ii + gd.NX * (jj + gd.NY * kk);
+            // slot of m in row-node n's neighbour list: neighbours of n that precede m
+            int slot = 0;
+            for (int64_t ek = (gd.dim == 3 ? -1 : 0); ek <= (gd.dim == 3 ? 1 : 0); ++ek)
+              for (int64_t ej = -1; ej <= 1; ++ej)
+                for (int64_t ei = -1; ei <= 1; ++ei) {
+                  const int64_t a = ii + ei, bb = jj + ej, cc = kk + ek;
+                  if (a < 0 || a >= gd.NX || bb < 0 || bb >= gd.NY || cc < 0 || cc >= gd.NZ) continue;
+                  const int64_t q = a + gd.NX * (bb + gd.NY * cc);
+                  if (q < m) ++slot;
+                }
+            const int cnt = count(n);
+            for (int c = 0; c < nc; ++c) {
+              const int64_t pos = (int64_t)nc * nc * nbr_start[n] + (int64_t)c * nc * cnt + (int64_t)slot * nc + c2;
+              ents.push_back({h->block_of_node[n] * nc + c, pos});
+            }
+          }
+      std::sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b2) { return a.fdof < b2.fdof; });
+      for (const Ent& e : ents) h->export_map[out++] = e.pos;
+    }
+  }
+}
+
+int do_assemble(topopt_handle* h) {
+  TRY(build_pattern(h));
+  const long long total = (long long)h->nnodes * (h->dim == 3 ? 27 : 9);
+#define CALL(D, C) LAUNCH(h, (k_assemble<D, C>), grid_for(total, kWideGrid), h->g, h->d_nbr_start, h->d_E, h->d_nz, h->d_col)
+  DISPATCH(h, CALL);
+#undef CALL
+  TRY(check_launch(h, "k_assemble"));
+#define CALL(D, C) LAUNCH(h, (k_csr_absdiag<D, C>), kReduceBlocks, h->g, h->d_nbr_start, h->d_nz, (double*)nullptr, h->d_partials, h->d_st)
+  DISPATCH(h, CALL);
+#undef CALL
+  TRY(check_launch(h, "k_csr_absdiag"));
+  const unsigned char* gfixed = h->d_fixed + h->g.S;  // single GPU: local plane 1 == global plane 0
+  if (h->nc == 1)
+    LAUNCH(h, (k_csr_apply_bc<1>), grid_for(h->ndof, kWideGrid), (long long)h->ndof, h->d_rowptr, h->d_col, h->d_nz, gfixed, h->d_st, 1.0 / (double)h->ndof);
+  else if (h->nc == 2)
+    LAUNCH(h, (k_csr_apply_bc<2>), grid_for(h->ndof, kWideGrid), (long long)h->ndof, h->d_rowptr, h->d_col, h->d_nz, gfixed, h->d_st, 1.0 / (double)h->ndof);
+  else
+    LAUNCH(h, (k_csr_apply_bc<3>), grid_for(h->ndof, kWideGrid), (long long)h->ndof, h->d_rowptr, h->d_col, h->d_nz, gfixed, h->d_st, 1.0 / (double)h->ndof);
+  TRY(check_launch(h, "k_csr_apply_bc"));
+  h->assembled = true;
+  h->stiffness_dirty = false;
+  return TOPOPT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int topopt_assemble(topopt_handle* h, double* nzval, double* f) {
+  if (!h) return fail(h, TOPOPT_ERR_INVALID, "topopt_assemble: NULL handle");
+  TRY(use_device(h));
+  TRY(do_assemble(h));
+  if (nzval) {
+    build_export_map(h);
+    std::vector<double> internal(h->nnz), outv(h->nnz);
+    CUDA_TRY(h, cudaMemcpyAsync(internal.data(), h->d_nz, sizeof(double) * h->nnz, cudaMemcpyDeviceToHost, h->stream));
+    TRY(sync(h));
+    for (int64_t k = 0; k < h->nnz; ++k) outv[k] = internal[h->export_map[k]];
+    CUDA_TRY(h, cudaMemcpyAsync(nzval, outv.data(), sizeof(double) * h->nnz, cudaMemcpyDefault, h->stream));
+    TRY(sync(h));
+    h->stats.d2h_bytes += sizeof(double) * h->nnz;
+  }
+  if (f) TRY(download_dofs(h, h->d_b, f));  // f = fixedload with prescribed entries zeroed (assemble.jl:51,87)
+  return sync(h);
+}
+
+int topopt_spmv(topopt_handle* h, const double* x, double* y) {
+  if (!h) return fail(h, TOPOPT_ERR_INVALID, "topopt_spmv: NULL handle");
+  TRY(use_device(h));
+  if (!h->assembled || h->stiffness_dirty) TRY(do_assemble(h));
+  if (x) TRY(upload_dofs(h, x, h->d_p));
+  TRY(launch_spmv<false>(h, h->d_p, h->d_Ap, FIN_NONE));
+  if (y) TRY(download_dofs(h, h->d_Ap, y));
+  return sync(h);
+}
+
+// ---- filters ------------------------------------------------------------------------------------
+int topopt_filter_create(topopt_handle* h, double rmin, topopt_filter** out) {
+  if (!h || !out) return fail(h, TOPOPT_ERR_INVALID, "topopt_filter_create: NULL argument");
+  *out = nullptr;
+  if (!(rmin > 0) || !std::isfinite(rmin)) return fail(h, TOPOPT_ERR_INVALID, "topopt_filter_create: rmin must be positive");
+  TRY(use_device(h));
+  topopt_filter* f = new topopt_filter();
+  f->h = h;
+  f->rmin = rmin;
+  FilterGeo& fg = f->fg;
+  const GridDims& gd = h->gd;
+  fg.dim = h->dim;
+  fg.nx = (int)gd.nx;
+  fg.ny = (int)gd.ny;
+  fg.nz = (int)gd.nz;
+  fg.NX = (int)gd.NX;
+  fg.NY = (int)gd.NY;
+  fg.NZ = (int)gd.NZ;
+  for (int a = 0; a < 3; ++a) fg.R[a] = 0;
+  for (int a = 0; a < h->dim; ++a) {
+    fg.R[a] = (int)std::ceil(rmin / h->sizes[a] + 0.5 + 1e-9) - 1;
+    if (fg.R[a] < 1) fg.R[a] = 1;
+    if (fg.R[a] > 64) {
+      delete f;
+      return fail(h, TOPOPT_ERR_INVALID, "topopt_filter_create: rmin spans more than 64 elements");
+    }
+  }
+  const int wx = 2 * fg.R[0], wy = 2 * fg.R[1], wz = h->dim == 3 ? 2 * fg.R[2] : 1;
+  std::vector<double> w((size_t)wx * wy * wz, 0.0);
+  double wsum = 0.0;
+  for (int tz = 0; tz < wz; ++tz)
+    for (int ty = 0; ty < wy; ++ty)
+      for (int tx = 0; tx < wx; ++tx) {
+        // node offset o = 1 - R + t from the cell index; distance to the centroid per axis (o - 1/2) h
+        const double ddx = (0.5 - fg.R[0] + tx) * h->sizes[0];
+        const double ddy = (0.5 - fg.R[1] + ty) * h->sizes[1];
+        const double ddz = h->dim == 3 ? (0.5 - fg.R[2] + tz) * h->sizes[2] : 0.0;
+        const double dist = std::sqrt(ddx * ddx + ddy * ddy + ddz * ddz);
+        const double wt = dist < rmin ? rmin - dist : 0.0;  // strict '<' (CheqFilters.jl:99)
+        w[tx + (size_t)wx * (ty + (size_t)wy * tz)] = wt;
+        wsum += wt;
+      }
+  if (wsum == 0.0) {
+    delete f;
+    return fail(h, TOPOPT_ERR_INVALID,
+                "DensityFilterFun: no neighbouring nodes were found within the filter radius `rmin` for any element; "
+                "increase `rmin` (mesh-coordinate units)");  // density_filter.jl:98-105
+  }
+  auto bail = [&](int rc) {
+    topopt_filter_destroy(f);
+    return rc;
+  };
+  int rc;
+  if ((rc = dev_alloc(h, &f->d_w, w.size())) != TOPOPT_OK) return bail(rc);
+  if ((rc = dev_alloc(h, &f->d_den, h->nel)) != TOPOPT_OK) return bail(rc);
+  if ((rc = dev_alloc(h, &f->d_nodal, h->nnodes)) != TOPOPT_OK) return bail(rc);
+  if ((rc = dev_alloc(h, &f->d_in, h->nel)) != TOPOPT_OK) return bail(rc);
+  if ((rc = dev_alloc(h, &f->d_out, h->nel)) != TOPOPT_OK) return bail(rc);
+  if (cudaMemcpyAsync(f->d_w, w.data(), sizeof(double) * w.size(), cudaMemcpyHostToDevice, h->stream) != cudaSuccess)
+    return bail(fail(h, TOPOPT_ERR_CUDA, "filter weight upload failed"));
+  LAUNCH(h, (k_filter_n2c<1>), grid_for(h->nel, kWideGrid), fg, f->d_w, (const double*)nullptr, (const double*)nullptr, f->d_den);
+  if ((rc = check_launch(h, "k_filter_n2c<1>")) != TOPOPT_OK) return bail(rc);
+  if ((rc = sync(h)) != TOPOPT_OK) return bail(rc);
+  *out = f;
+  return TOPOPT_OK;
+}
+
+int topopt_filter_apply(topopt_filter* f, const double* x, double* y, int32_t mode) {
+  if (!f) return fail(nullptr, TOPOPT_ERR_INVALID, "topopt_filter_apply: NULL filter");
+  topopt_handle* h = f->h;
+  if (mode != TOPOPT_FILTER_FORWARD && mode != TOPOPT_FILTER_TRANSPOSE) return fail(h, TOPOPT_ERR_INVALID, "topopt_filter_apply: bad mode");
+  TRY(use_device(h));
+  if (x) {
+    CUDA_TRY(h, cudaMemcpyAsync(f->d_in, x, sizeof(double) * h->nel, cudaMemcpyDefault, h->stream));
+    h->stats.h2d_bytes += sizeof(double) * h->nel;
+  }
+  CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+  TRY(filter_run(f, f->d_in, f->d_out, mode));
+  CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+  if (y) {
+    CUDA_TRY(h, cudaMemcpyAsync(y, f->d_out, sizeof(double) * h->nel, cudaMemcpyDefault, h->stream));
+    h->stats.d2h_bytes += sizeof(double) * h->nel;
+  }
+  TRY(sync(h));
+  float ms = 0;
+  CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->stats.last_filter_ms = ms;
+  return TOPOPT_OK;
+}
+
+int topopt_filter_destroy(topopt_filter* f) {
+  if (!f) return TOPOPT_OK;
+  cudaSetDevice(f->h->device);
+  cudaStreamSynchronize(f->h->stream);
+  for (void* p : {(void*)f->d_w, (void*)f->d_den, (void*)f->d_nodal, (void*)f->d_in, (void*)f->d_out})
+    if (p) cudaFree(p);
+  delete f;
+  return TOPOPT_OK;
+}
+
+// ---- fused SIMP evaluation --------------------------------------------------------------------
+int topopt_simp_eval(topopt_handle* h, topopt_filter* f, int32_t filter_kind, const double* x, int32_t penalty_kind, double p,
+                     double xmin, const topopt_cg_opts* opts, double* obj, double* grad_x, topopt_cg_result* result) {
+  if (!h || !opts) return fail(h, TOPOPT_ERR_INVALID, "topopt_simp_eval: NULL argument");
+  if (filter_kind < 0 || filter_kind > 2 || (filter_kind != 0 && (!f || f->h != h)))
+    return fail(h, TOPOPT_ERR_INVALID, "topopt_simp_eval: bad filter");
+  TRY(use_device(h));
+  if (x) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_design, x, sizeof(double) * h->nel, cudaMemcpyDefault, h->stream));
+    h->stats.h2d_bytes += sizeof(double) * h->nel;
+  }
+  const double* xf = h->d_design;
+  if (filter_kind == 1) {
+    TRY(filter_run(f, h->d_design, h->d_xf, TOPOPT_FILTER_FORWARD));
+    xf = h->d_xf;
+  }
+  TRY(upload_elems(h, xf, h->d_rho, false));
+  TRY(penalize(h, penalty_kind, p, xmin, 1));
+  TRY(cg_solve(h, h->d_b, opts, result));
+  TRY(run_sens(h, h->d_u, h->d_u, -1.0, obj));
+  double* gfull = nullptr;
+  TRY(gather_elems_device(h, h->d_grad, &gfull));
+  const double* gout = gfull;
+  if (filter_kind != 0) {
+    TRY(filter_run(f, gfull, h->d_gfull, filter_kind == 1 ? TOPOPT_FILTER_TRANSPOSE : TOPOPT_FILTER_FORWARD));
+    gout = h->d_gfull;
+  }
+  if (grad_x) {
+    CUDA_TRY(h, cudaMemcpyAsync(grad_x, gout, sizeof(double) * h->nel, cudaMemcpyDefault, h->stream));
+    h->stats.d2h_bytes += sizeof(double) * h->nel;
+  }
+  return sync(h);
+}
+
+// ---- measurement ------------------------------------------------------------------------------
+int topopt_time_kernel(topopt_handle* h, topopt_filter* f, int32_t which, int32_t reps, double* ms_out) {
+  if (!h || !ms_out || reps < 1) return fail(h, TOPOPT_ERR_INVALID, "topopt_time_kernel: bad argument");
+  TRY(use_device(h));
+  topopt_cg_opts o{};
+  o.abstol = 0;
+  o.reltol = 0;
+  o.maxiter = reps;
+  o.check_every = reps;
+  float ms = 0;
+  switch (which) {
+    case 0:
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_p, h->d_b, sizeof(double) * h->nloc_dofs, cudaMemcpyDeviceToDevice, h->stream));
+      CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+      for (int r = 0; r < reps; ++r) TRY(launch_apply<false>(h, h->d_p, h->d_Ap, FIN_NONE));
+      CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+      break;
+    case 1:
+    case 6: {
+      o.op = which == 6 ? TOPOPT_OP_ASSEMBLED : TOPOPT_OP_MATRIX_FREE;
+      topopt_cg_result r{};
+      TRY(cg_solve(h, h->d_b, &o, &r, true, reps));
+      *ms_out = r.solve_ms / std::max(1, r.iters);
+      return TOPOPT_OK;
+    }
+    case 2:
+      CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+      for (int r = 0; r < reps; ++r) {
+#define CALL(D, C) \
+  LAUNCH(h, (k_sens<D, C>), kReduceBlocks, h->g, h->d_u, h->d_u, h->d_E, h->d_dE, h->d_cell, h->d_grad, -1.0, h->d_partials, h->d_st)
+        DISPATCH(h, CALL);
+#undef CALL
+      }
+      CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+      break;
+    case 3:
+      if (!f) return fail(h, TOPOPT_ERR_INVALID, "topopt_time_kernel: filter needed");
+      CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+      for (int r = 0; r < reps; ++r) TRY(filter_run(f, h->d_design, h->d_xf, TOPOPT_FILTER_FORWARD));
+      CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+      break;
+    case 4:
+      if (!h->assembled || h->stiffness_dirty) TRY(do_assemble(h));
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_p, h->d_b, sizeof(double) * h->nloc_dofs, cudaMemcpyDeviceToDevice, h->stream));
+      CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+      for (int r = 0; r < reps; ++r) TRY(launch_spmv<false>(h, h->d_p, h->d_Ap, FIN_NONE));
+      CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+      break;
+    case 5:
+      TRY(do_assemble(h));
+      CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+      for (int r = 0; r < reps; ++r) TRY(do_assemble(h));
+      CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+      break;
+    default:
+      return fail(h, TOPOPT_ERR_INVALID, "topopt_time_kernel: unknown kernel class");
+  }
+  TRY(check_launch(h, "topopt_time_kernel"));
+  TRY(sync(h));
+  CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  *ms_out = ms / reps;
+  return TOPOPT_OK;
+}
+
+}  // extern "C"

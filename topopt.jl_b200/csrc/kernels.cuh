@@ -1,0 +1,774 @@
+// Device kernels of libtopopt_cuda (fp64, sm_100a).  All kernels are atomic-free on the data
+// path and deterministic: reductions go through fixed-order per-block partials that the last
+// block to finish sums in a fixed order.
+//
+// Data layout (per rank): nodes lexicographic (x fastest), dofs interleaved per node
+// (ncomp*node + c); the grid is cut into slabs along the last axis.  A rank stores its owned
+// node planes 1..nown plus one ghost plane on each side (local planes 0 and nown+1) and its
+// owned element layers 1..nlay plus one ghost layer below (local layer 0).  Local layer l
+// touches local node planes l and l+1.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace topopt {
+
+struct Geo {
+  int NX, NY;      // nodes per in-plane axis (NY = 1 in 2-D)
+  int nx, ny;      // elements per in-plane axis (ny = 1 in 2-D)
+  int S, SE;       // nodes per plane, elements per layer
+  int NPg, NLg;    // global number of node planes / element layers along the slab axis
+  int p0;          // global index of local plane 0 ( = global index of local layer 0 ); may be -1
+  int nown;        // owned node planes (local 1..nown)
+  int nlay;        // owned element layers (local 1..nlay)
+};
+
+struct CGState {
+  double sums[8];   // this rank's reduction results
+  double gsums[8];  // after the allreduce (aliases sums when world == 1)
+  double res, prev_res, rho, rho_prev, alpha, beta, tol, abstol, reltol, energy, pAp;
+  int iters, done, converged, maxiter, criteria, precond, nonfinite, world;
+  unsigned int counter;
+};
+
+constexpr int kMaxKe = 24;
+__constant__ double cKe[kMaxKe * kMaxKe];  // shared element matrix, column-major
+
+constexpr int kBlock = 256;
+constexpr int kReduceBlocks = 148 * 4;  // persistent grid for vector kernels (multiple of the SM count)
+
+// ---- reductions ---------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// sum over the block; result valid in thread 0.  sm must hold 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* sm) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = (lane < (blockDim.x >> 5)) ? sm[lane] : 0.0;
+    v = warp_sum(v);
+  }
+  return v;
+}
+
+enum { FIN_NONE = 0, FIN_INIT = 1, FIN_PAP = 2, FIN_RR = 3, FIN_PLAIN = 4 };
+
+// scalar recurrences of IterativeSolvers.cg! (CGIterable / PCGIterable iterate) and the
+// convergence tests of src/FEA/convergence_criteria.jl:26-45, evaluated on the device so the
+// host never has to synchronise inside the loop.
+__device__ inline void cg_finalize(CGState* st, int which) {
+  const double* s = st->gsums;
+  if (which == FIN_PAP) {
+    st->pAp = s[0];
+    st->alpha = st->precond ? st->rho / s[0] : (st->res * st->res) / s[0];
+    return;
+  }
+  if (which == FIN_INIT) {
+    st->res = sqrt(s[0]);
+    st->tol = fmax(st->reltol * st->res, st->abstol);
+    st->prev_res = 1.0;
+    st->rho_prev = 1.0;
+    st->energy = 0.0;
+    st->iters = 0;
+  } else {  // FIN_RR
+    st->prev_res = st->res;
+    st->res = sqrt(s[0]);
+    st->iters += 1;
+  }
+  if (st->precond) {
+    if (which == FIN_RR) st->rho_prev = st->rho;
+    st->rho = s[1];
+    st->beta = st->rho / st->rho_prev;
+  } else {
+    st->beta = (st->res * st->res) / (st->prev_res * st->prev_res);
+  }
+  bool conv;
+  if (st->criteria == 0) {
+    conv = st->res <= st->tol;
+  } else {
+    const double xtr = s[2];
+    const double xAx = s[3] - xtr;
+    const double change = xAx - st->energy;
+    if (isnan(change) || isnan(xAx) || xAx < 0.0) st->nonfinite = 1;
+    conv = (fabs(change) / xAx <= st->tol) && (fabs(xtr) / xAx <= st->tol);
+    st->energy = xAx;
+  }
+  if (isnan(st->res)) st->nonfinite = 1;
+  st->converged = conv ? 1 : 0;
+  st->done = (conv || st->iters >= st->maxiter || st->nonfinite) ? 1 : 0;
+}
+
+// Each block deposits NS partial sums; the last block to arrive adds all partials in a fixed
+// order, publishes them and (single-GPU) runs the scalar step.
+template <int NS>
+__device__ __forceinline__ void block_partials_finish(const double (&v)[NS], double* partials,
+                                                      CGState* st, int which, double* sm) {
+  __shared__ bool is_last;
+  double r[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) r[k] = block_sum(v[k], sm);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) partials[blockIdx.x * NS + k] = r[k];
+    __threadfence();
+    const unsigned int t = atomicInc(&st->counter, gridDim.x - 1);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double a[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) a[k] = 0.0;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) a[k] += __ldcg(&partials[b * NS + k]);
+  }
+#pragma unroll
+  for (int k = 0; k < NS; ++k) a[k] = block_sum(a[k], sm);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) st->sums[k] = a[k];
+    if (st->world == 1 && which != FIN_NONE && which != FIN_PLAIN) {
+#pragma unroll
+      for (int k = 0; k < NS; ++k) st->gsums[k] = a[k];
+      cg_finalize(st, which);
+    }
+  }
+}
+
+__global__ void k_finalize(CGState* st, int which) {
+  if (which == FIN_INIT || !st->done) cg_finalize(st, which);
+}
+
+// ---- layout conversion at the ABI edge -----------------------------------------------------
+// local (lexicographic slab, ghosts included) <- full Ferrite-ordered vector
+template <int NC>
+__global__ void k_gather_dofs(Geo g, const int* __restrict__ block_of_node, const double* __restrict__ full,
+                              double* __restrict__ loc) {
+  const long long nloc = (long long)g.S * (g.nown + 2);
+  for (long long ln = blockIdx.x * (long long)blockDim.x + threadIdx.x; ln < nloc;
+       ln += (long long)gridDim.x * blockDim.x) {
+    const int lp = (int)(ln / g.S);
+    const int gp = lp + g.p0;
+    if (gp < 0 || gp >= g.NPg) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) loc[ln * NC + c] = 0.0;
+      continue;
+    }
+    const long long b = block_of_node[ln];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) loc[ln * NC + c] = full[b * NC + c];
+  }
+}
+
+// full Ferrite-ordered vector <- owned part of a local vector
+template <int NC>
+__global__ void k_scatter_dofs(Geo g, const int* __restrict__ block_of_node, const double* __restrict__ loc,
+                               double* __restrict__ full) {
+  const long long nown = (long long)g.S * g.nown;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nown;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long ln = t + g.S;
+    const long long b = block_of_node[ln];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) full[b * NC + c] = loc[ln * NC + c];
+  }
+}
+
+// ---- penalisation (src/Utilities/penalties.jl:30-54,113-130; utils.jl:77) ------------------
+__global__ void k_penalize(long long n, const double* __restrict__ rho, double* __restrict__ E,
+                           double* __restrict__ dE, int kind, double p, double xmin, int pen_first) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    const double x = rho[e];
+    const double a = pen_first ? x : x * (1.0 - xmin) + xmin;  // argument of the penalty
+    double f, df;
+    if (kind == 0) {  // x^p
+      f = pow(a, p);
+      df = p * pow(a, p - 1.0);
+    } else if (kind == 1) {  // x / (1 + p (1 - x))
+      const double d = 1.0 + p * (1.0 - a);
+      f = a / d;
+      df = (1.0 + p) / (d * d);
+    } else {  // sinh(p x) / sinh(p)
+      const double s = sinh(p);
+      f = sinh(p * a) / s;
+      df = p * cosh(p * a) / s;
+    }
+    if (pen_first) {
+      E[e] = f * (1.0 - xmin) + xmin;
+      dE[e] = (1.0 - xmin) * df;
+    } else {
+      E[e] = f;
+      dE[e] = df * (1.0 - xmin);
+    }
+  }
+}
+
+// ---- matrix-free operator -------------------------------------------------------------------
+template <int DIM>
+__host__ __device__ constexpr int corner_local(int ox, int oy, int op) {
+  // Ferrite local node of corner (ox, oy, op); in 2-D the slab axis (op) is y.
+  return DIM == 3 ? (((ox ^ oy) | (oy << 1)) + 4 * op) : ((ox ^ op) | (op << 1));
+}
+
+// y = K(E) x, node-centric gather (matrix_free_operator.jl:66-105): for each of the <= 2^DIM
+// adjacent elements (ascending cell id) accumulate row(Ke_bc) . x_e, scale by E_e, then add the
+// element contributions in ascending cell order.  Prescribed rows return fixed_diag * x.
+// DOT: also reduce sum_owned x.y into partials and run the CG scalar step `fin`.
+template <int DIM, int NC, bool DOT>
+__global__ void __launch_bounds__(kBlock) k_apply(Geo g, const double* __restrict__ x, double* __restrict__ y,
+                                                  const double* __restrict__ E,
+                                                  const unsigned char* __restrict__ fixed, double fixed_diag,
+                                                  double* partials, CGState* st, int fin) {
+  constexpr int NQ = 1 << DIM;
+  constexpr int KS = NQ * NC;
+  constexpr int NYR = DIM == 3 ? 3 : 1;
+  constexpr int NEY = DIM == 3 ? 2 : 1;
+  __shared__ double sm[32];
+  if (DOT && st->done) return;
+  const long long nown = (long long)g.S * g.nown;
+  double dot = 0.0;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nown;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int inpl = (int)(t % g.S);
+    const int lp = (int)(t / g.S) + 1;
+    const int i = inpl % g.NX;
+    const int j = DIM == 3 ? inpl / g.NX : 0;
+    const int gk = lp + g.p0;  // global plane
+    double Eq[NQ];
+    double acc[NQ][NC];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int ex = q & 1, ey = DIM == 3 ? (q >> 1) & 1 : 0, ep = DIM == 3 ? (q >> 2) & 1 : (q >> 1) & 1;
+      const int ei = i - 1 + ex, ej = j - 1 + ey, el = lp - 1 + ep, egl = gk - 1 + ep;
+      bool ok = ei >= 0 && ei < g.nx && egl >= 0 && egl < g.NLg;
+      if (DIM == 3) ok = ok && ej >= 0 && ej < g.ny;
+      Eq[q] = ok ? E[(long long)el * g.SE + (DIM == 3 ? ej * g.nx : 0) + ei] : 0.0;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[q][c] = 0.0;
+    }
+    double xo[NC];
+    unsigned char fo = 0;
+#pragma unroll
+    for (int dp = 0; dp < 3; ++dp) {
+#pragma unroll
+      for (int dy = 0; dy < NYR; ++dy) {
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const int ii = i - 1 + dx, jj = DIM == 3 ? j - 1 + dy : 0, pp = lp - 1 + dp, gp = gk - 1 + dp;
+          bool ok = ii >= 0 && ii < g.NX && gp >= 0 && gp < g.NPg;
+          if (DIM == 3) ok = ok && jj >= 0 && jj < g.NY;
+          double xb[NC];
+          unsigned char fb = 0;
+          if (ok) {
+            const long long ln = (long long)pp * g.S + (long long)jj * g.NX + ii;
+            fb = fixed[ln];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) xb[c] = x[ln * NC + c];
+          } else {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) xb[c] = 0.0;
+          }
+          if (dp == 1 && dx == 1 && (DIM == 2 || dy == 1)) {
+            fo = fb;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) xo[c] = xb[c];
+          }
+#pragma unroll
+          for (int c = 0; c < NC; ++c)
+            if (fb & (1 << c)) xb[c] = 0.0;  // bcmatrix: constrained columns are zero
+#pragma unroll
+          for (int ep = 0; ep < 2; ++ep) {
+            const int op = dp - ep;
+            if (op < 0 || op > 1) continue;
+#pragma unroll
+            for (int ey = 0; ey < NEY; ++ey) {
+              const int oy = DIM == 3 ? dy - ey : 0;
+              if (oy < 0 || oy > 1) continue;
+#pragma unroll
+              for (int ex = 0; ex < 2; ++ex) {
+                const int ox = dx - ex;
+                if (ox < 0 || ox > 1) continue;
+                const int q = DIM == 3 ? ex + 2 * ey + 4 * ep : ex + 2 * ep;
+                const int aloc = corner_local<DIM>(1 - ex, 1 - ey, 1 - ep);
+                const int bloc = corner_local<DIM>(ox, oy, op);
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+#pragma unroll
+                  for (int c2 = 0; c2 < NC; ++c2)
+                    acc[q][c] = fma(cKe[(NC * aloc + c) + KS * (NC * bloc + c2)], xb[c2], acc[q][c]);
+              }
+            }
+          }
+        }
+      }
+    }
+    const long long ln = (long long)lp * g.S + inpl;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      double v = 0.0;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) v += Eq[q] * acc[q][c];
+      if (fo & (1 << c)) v = fixed_diag * xo[c];
+      y[ln * NC + c] = v;
+      if (DOT) dot = fma(xo[c], v, dot);
+    }
+  }
+  if (DOT) {
+    const double v[1] = {dot};
+    block_partials_finish<1>(v, partials, st, fin, sm);
+  }
+}
+
+// diagonal of K(E) on owned dofs (Jacobi preconditioner)
+template <int DIM, int NC>
+__global__ void k_diag(Geo g, double* __restrict__ d, const double* __restrict__ E,
+                       const unsigned char* __restrict__ fixed, double fixed_diag) {
+  constexpr int NQ = 1 << DIM;
+  constexpr int KS = NQ * NC;
+  const long long nown = (long long)g.S * g.nown;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nown;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int inpl = (int)(t % g.S);
+    const int lp = (int)(t / g.S) + 1;
+    const int i = inpl % g.NX;
+    const int j = DIM == 3 ? inpl / g.NX : 0;
+    const int gk = lp + g.p0;
+    const long long ln = (long long)lp * g.S + inpl;
+    const unsigned char fo = fixed[ln];
+    double acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int ex = q & 1, ey = DIM == 3 ? (q >> 1) & 1 : 0, ep = DIM == 3 ? (q >> 2) & 1 : (q >> 1) & 1;
+      const int ei = i - 1 + ex, ej = j - 1 + ey, el = lp - 1 + ep, egl = gk - 1 + ep;
+      bool ok = ei >= 0 && ei < g.nx && egl >= 0 && egl < g.NLg;
+      if (DIM == 3) ok = ok && ej >= 0 && ej < g.ny;
+      if (!ok) continue;
+      const double Ee = E[(long long)el * g.SE + (DIM == 3 ? ej * g.nx : 0) + ei];
+      const int aloc = corner_local<DIM>(1 - ex, 1 - ey, 1 - ep);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[c] += Ee * cKe[(NC * aloc + c) * (KS + 1)];
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) d[ln * NC + c] = (fo & (1 << c)) ? fixed_diag : acc[c];
+  }
+}
+
+// ---- CG vector kernels (IterativeSolvers cg!, see cg_finalize) --------------------------------
+// r = b, x = 0, p = 0 on owned dofs; sums: r.r [, r.(r/D)]
+__global__ void __launch_bounds__(kBlock) k_cg_init(long long off, long long n, const double* __restrict__ b,
+                                                    double* __restrict__ x, double* __restrict__ r,
+                                                    double* __restrict__ p, const double* __restrict__ D,
+                                                    double* partials, CGState* st) {
+  __shared__ double sm[32];
+  double v[2] = {0.0, 0.0};
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long k = off + t;
+    const double bv = b[k];
+    r[k] = bv;
+    x[k] = 0.0;
+    p[k] = 0.0;
+    v[0] = fma(bv, bv, v[0]);
+    if (D) v[1] = fma(bv, bv / D[k], v[1]);
+  }
+  block_partials_finish<2>(v, partials, st, FIN_INIT, sm);
+}
+
+// p = z + beta p   (z = r, or r/D when preconditioned)
+__global__ void __launch_bounds__(kBlock) k_update_p(long long off, long long n, const double* __restrict__ r,
+                                                     double* __restrict__ p, const double* __restrict__ D,
+                                                     const CGState* __restrict__ st) {
+  if (st->done) return;
+  const double beta = st->beta;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long k = off + t;
+    const double z = D ? r[k] / D[k] : r[k];
+    p[k] = fma(beta, p[k], z);
+  }
+}
+
+// x += alpha p ; r -= alpha Ap ; sums: r.r, r.(r/D), x.r, b.x
+template <bool ENERGY>
+__global__ void __launch_bounds__(kBlock) k_update_xr(long long off, long long n, double* __restrict__ x,
+                                                      double* __restrict__ r, const double* __restrict__ p,
+                                                      const double* __restrict__ Ap, const double* __restrict__ D,
+                                                      const double* __restrict__ b, double* partials,
+                                                      CGState* st) {
+  __shared__ double sm[32];
+  if (st->done) return;
+  const double alpha = st->alpha;
+  double v[4] = {0.0, 0.0, 0.0, 0.0};
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long k = off + t;
+    const double xv = fma(alpha, p[k], x[k]);
+    const double rv = fma(-alpha, Ap[k], r[k]);
+    x[k] = xv;
+    r[k] = rv;
+    v[0] = fma(rv, rv, v[0]);
+    if (D) v[1] = fma(rv, rv / D[k], v[1]);
+    if (ENERGY) {
+      v[2] = fma(xv, rv, v[2]);
+      v[3] = fma(b[k], xv, v[3]);
+    }
+  }
+  block_partials_finish<4>(v, partials, st, FIN_RR, sm);
+}
+
+// plain dot over owned dofs -> st->sums[0]
+__global__ void __launch_bounds__(kBlock) k_dot(long long off, long long n, const double* __restrict__ a,
+                                                const double* __restrict__ b, double* partials, CGState* st) {
+  __shared__ double sm[32];
+  double v[1] = {0.0};
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
+       t += (long long)gridDim.x * blockDim.x)
+    v[0] = fma(a[off + t], b[off + t], v[0]);
+  block_partials_finish<1>(v, partials, st, FIN_PLAIN, sm);
+}
+
+__global__ void k_zero_entries(long long n, const int* __restrict__ idx, double* __restrict__ v) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
+       t += (long long)gridDim.x * blockDim.x)
+    v[idx[t]] = 0.0;
+}
+
+// zero prescribed dofs of a local vector using the node flags (apply_zero!)
+template <int NC>
+__global__ void k_apply_zero(long long nnodes_loc, const unsigned char* __restrict__ fixed, double* __restrict__ v) {
+  for (long long ln = blockIdx.x * (long long)blockDim.x + threadIdx.x; ln < nnodes_loc;
+       ln += (long long)gridDim.x * blockDim.x) {
+    const unsigned char f = fixed[ln];
+    if (!f) continue;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      if (f & (1 << c)) v[ln * NC + c] = 0.0;
+  }
+}
+
+// ---- compliance / sensitivity (compute_element_energy.jl:18-38, thermal_compliance.jl:144-155)
+// c_e = v_e' Ke u_e with the raw Ke (v = u for compliance); grad_e = gsign * dE_e c_e;
+// sums[0] = sum E_e c_e.
+template <int DIM, int NC>
+__global__ void __launch_bounds__(kBlock) k_sens(Geo g, const double* __restrict__ u, const double* __restrict__ v,
+                                                 const double* __restrict__ E, const double* __restrict__ dE,
+                                                 double* __restrict__ cell, double* __restrict__ grad, double gsign,
+                                                 double* partials, CGState* st) {
+  constexpr int NQ = 1 << DIM;
+  constexpr int KS = NQ * NC;
+  __shared__ double sm[32];
+  const long long nel = (long long)g.SE * g.nlay;
+  double obj[1] = {0.0};
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nel;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int inl = (int)(t % g.SE);
+    const int ll = (int)(t / g.SE) + 1;
+    const int i = inl % g.nx;
+    const int j = DIM == 3 ? inl / g.nx : 0;
+    double ue[KS], ve[KS];
+#pragma unroll
+    for (int a = 0; a < NQ; ++a) {
+      // inverse of corner_local: local node a -> corner offsets
+      const int az = DIM == 3 ? a >> 2 : 0;
+      const int a4 = a & 3;
+      const int o2 = a4 >> 1;          // second in-ring axis
+      const int ox = (a4 & 1) ^ o2;    // x
+      const int oy = DIM == 3 ? o2 : 0;
+      const int op = DIM == 3 ? az : o2;
+      const long long ln = (long long)(ll + op) * g.S + (long long)(j + oy) * g.NX + (i + ox);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        ue[a * NC + c] = u[ln * NC + c];
+        ve[a * NC + c] = v[ln * NC + c];
+      }
+    }
+    double ce = 0.0;
+#pragma unroll
+    for (int w = 0; w < KS; ++w) {
+#pragma unroll
+      for (int r = 0; r < KS; ++r) ce = fma(ve[r] * cKe[r + KS * w], ue[w], ce);
+    }
+    const long long le = (long long)ll * g.SE + inl;
+    if (cell) cell[le] = ce;
+    if (grad) grad[le] = gsign * dE[le] * ce;
+    obj[0] = fma(E[le], ce, obj[0]);
+  }
+  block_partials_finish<1>(obj, partials, st, FIN_PLAIN, sm);
+}
+
+// ---- filter (CheqFilters.jl:66-118, density_filter.jl:49-108, sens_filter.jl:72-110) ---------
+// On a uniform grid the reference's two stages collapse to
+//   s_n = sum_{c in cells(n)} x_c                       (cell -> node; the 1/m_n of the mean cancels
+//   y_i = sum_n w(n-i) s_n / den_i                       against the duplicate multiplicity m_n)
+//   den_i = sum_n m_n w(n-i),  w = max(rmin - dist, 0) for dist < rmin, m_n = |cells(n)|.
+struct FilterGeo {
+  int nx, ny, nz;  // cells
+  int NX, NY, NZ;  // nodes
+  int R[3];        // node offsets o in [1-R, R] per axis (R[2] = 0 -> single plane in 2-D)
+  int dim;
+};
+
+__global__ void k_filter_c2n(FilterGeo f, const double* __restrict__ x, double* __restrict__ s) {
+  const long long nn = (long long)f.NX * f.NY * f.NZ;
+  for (long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x; n < nn;
+       n += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(n % f.NX), j = (int)((n / f.NX) % f.NY), k = (int)(n / ((long long)f.NX * f.NY));
+    double acc = 0.0;
+    for (int dk = (f.dim == 3 ? -1 : 0); dk <= 0; ++dk)
+      for (int dj = -1; dj <= 0; ++dj)
+        for (int di = -1; di <= 0; ++di) {
+          const int ci = i + di, cj = j + dj, ck = k + dk;
+          if (ci < 0 || ci >= f.nx || cj < 0 || cj >= f.ny || ck < 0 || ck >= f.nz) continue;
+          acc += x[ci + (long long)f.nx * (cj + (long long)f.ny * ck)];
+        }
+    s[n] = acc;
+  }
+}
+
+// MODE 0: y_i = sum_n w s_n / den_i ; MODE 1: den_i = sum_n m_n w (setup)
+template <int MODE>
+__global__ void k_filter_n2c(FilterGeo f, const double* __restrict__ wtab, const double* __restrict__ s,
+                             const double* __restrict__ den, double* __restrict__ y) {
+  const long long ne = (long long)f.nx * f.ny * f.nz;
+  const int wx = 2 * f.R[0], wy = 2 * f.R[1], wz = f.dim == 3 ? 2 * f.R[2] : 1;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < ne;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e % f.nx), j = (int)((e / f.nx) % f.ny), k = (int)(e / ((long long)f.nx * f.ny));
+    double acc = 0.0;
+    for (int tz = 0; tz < wz; ++tz) {
+      const int nk = f.dim == 3 ? k + 1 - f.R[2] + tz : 0;
+      if (nk < 0 || nk >= f.NZ) continue;
+      const int mz = (f.dim == 3 && nk > 0 && nk < f.NZ - 1) ? 2 : 1;
+      for (int ty = 0; ty < wy; ++ty) {
+        const int nj = j + 1 - f.R[1] + ty;
+        if (nj < 0 || nj >= f.NY) continue;
+        const int my = (nj > 0 && nj < f.NY - 1) ? 2 : 1;
+        for (int tx = 0; tx < wx; ++tx) {
+          const int ni = i + 1 - f.R[0] + tx;
+          if (ni < 0 || ni >= f.NX) continue;
+          const double w = wtab[tx + wx * (ty + wy * tz)];
+          if (MODE == 0) {
+            acc = fma(w, s[ni + (long long)f.NX * (nj + (long long)f.NY * nk)], acc);
+          } else {
+            const int mx = (ni > 0 && ni < f.NX - 1) ? 2 : 1;
+            acc = fma(w, (double)(mx * my * mz), acc);
+          }
+        }
+      }
+    }
+    y[e] = MODE == 0 ? acc / den[e] : acc;
+  }
+}
+
+// transpose, stage 2': t_n = sum_i w(n-i) d_i / den_i   (gather over cells around node n)
+__global__ void k_filter_c2n_T(FilterGeo f, const double* __restrict__ wtab, const double* __restrict__ d,
+                               const double* __restrict__ den, double* __restrict__ t) {
+  const long long nn = (long long)f.NX * f.NY * f.NZ;
+  const int wx = 2 * f.R[0], wy = 2 * f.R[1], wz = f.dim == 3 ? 2 * f.R[2] : 1;
+  for (long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x; n < nn;
+       n += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(n % f.NX), j = (int)((n / f.NX) % f.NY), k = (int)(n / ((long long)f.NX * f.NY));
+    double acc = 0.0;
+    // node n = cell + 1 - R + t  ->  cell = n - 1 + R - t
+    for (int tz = 0; tz < wz; ++tz) {
+      const int ck = f.dim == 3 ? k - 1 + f.R[2] - tz : 0;
+      if (ck < 0 || ck >= f.nz) continue;
+      for (int ty = 0; ty < wy; ++ty) {
+        const int cj = j - 1 + f.R[1] - ty;
+        if (cj < 0 || cj >= f.ny) continue;
+        for (int tx = 0; tx < wx; ++tx) {
+          const int ci = i - 1 + f.R[0] - tx;
+          if (ci < 0 || ci >= f.nx) continue;
+          const long long e = ci + (long long)f.nx * (cj + (long long)f.ny * ck);
+          acc = fma(wtab[tx + wx * (ty + wy * tz)], d[e] / den[e], acc);
+        }
+      }
+    }
+    t[n] = acc;
+  }
+}
+
+// transpose, stage 1': y_c = sum_{n in c} t_n
+__global__ void k_filter_n2c_T(FilterGeo f, const double* __restrict__ t, double* __restrict__ y) {
+  const long long ne = (long long)f.nx * f.ny * f.nz;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < ne;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e % f.nx), j = (int)((e / f.nx) % f.ny), k = (int)(e / ((long long)f.nx * f.ny));
+    double acc = 0.0;
+    for (int dk = 0; dk <= (f.dim == 3 ? 1 : 0); ++dk)
+      for (int dj = 0; dj <= 1; ++dj)
+        for (int di = 0; di <= 1; ++di) acc += t[(i + di) + (long long)f.NX * ((j + dj) + (long long)f.NY * (k + dk))];
+    y[e] = acc;
+  }
+}
+
+// ---- assembled path (assemble.jl:28-90; Ferrite assemble!/apply!) -----------------------------
+// Internal CSR in lexicographic dof order.  Row (n,c) holds, for every in-range neighbour node m
+// (z,y,x ascending) and component c2, K[(n,c),(m,c2)].  nbr_start[n] = number of (node,neighbour)
+// pairs before node n, so row (n,c) starts at NC*NC*nbr_start[n] + c*NC*cnt(n).
+template <int DIM>
+__device__ __forceinline__ int nbr_count(const Geo& g, int i, int j, int k) {
+  const int cx = 1 + (i > 0) + (i < g.NX - 1);
+  const int cp = 1 + (k > 0) + (k < g.NPg - 1);
+  if (DIM == 2) return cx * cp;
+  const int cy = 1 + (j > 0) + (j < g.NY - 1);
+  return cx * cy * cp;
+}
+
+// one thread per (node, neighbour offset): value = sum over shared elements (ascending cell id)
+// of fl(E_e * Ke[a,b]) -- the exact arithmetic of Ferrite's assemble!(assembler, dofs, px*Ke).
+template <int DIM, int NC>
+__global__ void k_assemble(Geo g, const long long* __restrict__ nbr_start, const double* __restrict__ E,
+                           double* __restrict__ nz, int* __restrict__ col) {
+  constexpr int NQ = 1 << DIM;
+  constexpr int KS = NQ * NC;
+  constexpr int NN = DIM == 3 ? 27 : 9;
+  const long long total = (long long)g.S * g.NPg * NN;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long n = t / NN;
+    const int o = (int)(t % NN);
+    const int dx = o % 3, dy = DIM == 3 ? (o / 3) % 3 : 1, dp = DIM == 3 ? o / 9 : o / 3;
+    const int inpl = (int)(n % g.S), k = (int)(n / g.S);
+    const int i = inpl % g.NX, j = DIM == 3 ? inpl / g.NX : 0;
+    const int ii = i - 1 + dx, jj = DIM == 3 ? j - 1 + dy : 0, kk = k - 1 + dp;
+    bool ok = ii >= 0 && ii < g.NX && kk >= 0 && kk < g.NPg;
+    if (DIM == 3) ok = ok && jj >= 0 && jj < g.NY;
+    if (!ok) continue;
+    // slot of this neighbour among the valid ones (z,y,x ascending)
+    int slot = 0;
+    for (int o2 = 0; o2 < o; ++o2) {
+      const int ex = o2 % 3, ey = DIM == 3 ? (o2 / 3) % 3 : 1, ez = DIM == 3 ? o2 / 9 : o2 / 3;
+      const int a = i - 1 + ex, b = DIM == 3 ? j - 1 + ey : 0, c = k - 1 + ez;
+      bool v = a >= 0 && a < g.NX && c >= 0 && c < g.NPg;
+      if (DIM == 3) v = v && b >= 0 && b < g.NY;
+      slot += v ? 1 : 0;
+    }
+    const int cnt = nbr_count<DIM>(g, i, j, k);
+    double val[NC][NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int c2 = 0; c2 < NC; ++c2) val[c][c2] = 0.0;
+    for (int q = 0; q < NQ; ++q) {  // ascending cell id
+      const int ex = q & 1, ey = DIM == 3 ? (q >> 1) & 1 : 0, ep = DIM == 3 ? (q >> 2) & 1 : (q >> 1) & 1;
+      const int ox = dx - ex, oy = DIM == 3 ? dy - ey : 0, op = dp - ep;
+      if (ox < 0 || ox > 1 || oy < 0 || oy > 1 || op < 0 || op > 1) continue;
+      const int ei = i - 1 + ex, ej = j - 1 + ey, el = k - 1 + ep;
+      bool eok = ei >= 0 && ei < g.nx && el >= 0 && el < g.NLg;
+      if (DIM == 3) eok = eok && ej >= 0 && ej < g.ny;
+      if (!eok) continue;
+      // single-GPU path: local layer index = global layer + 1 (ghost layer 0)
+      const double Ee = E[(long long)(el + 1) * g.SE + (DIM == 3 ? ej * g.nx : 0) + ei];
+      const int aloc = corner_local<DIM>(1 - ex, 1 - ey, 1 - ep);
+      const int bloc = corner_local<DIM>(ox, oy, op);
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int c2 = 0; c2 < NC; ++c2)
+          val[c][c2] = __dadd_rn(val[c][c2], __dmul_rn(Ee, cKe[(NC * aloc + c) + KS * (NC * bloc + c2)]));
+    }
+    const long long m = (long long)kk * g.S + (long long)jj * g.NX + ii;
+    const long long base = (long long)NC * NC * nbr_start[n];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int c2 = 0; c2 < NC; ++c2) {
+        const long long pos = base + (long long)c * NC * cnt + slot * NC + c2;
+        nz[pos] = val[c][c2];
+        col[pos] = (int)(m * NC + c2);
+      }
+  }
+}
+
+// sum |K_dd| over all rows -> st->sums[0]  (Ferrite meandiag numerator)
+template <int DIM, int NC>
+__global__ void __launch_bounds__(kBlock) k_csr_absdiag(Geo g, const long long* __restrict__ nbr_start,
+                                                        const double* __restrict__ nz, double* __restrict__ diag,
+                                                        double* partials, CGState* st) {
+  __shared__ double sm[32];
+  const long long nn = (long long)g.S * g.NPg;
+  double v[1] = {0.0};
+  for (long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x; n < nn;
+       n += (long long)gridDim.x * blockDim.x) {
+    const int inpl = (int)(n % g.S), k = (int)(n / g.S);
+    const int i = inpl % g.NX, j = DIM == 3 ? inpl / g.NX : 0;
+    const int cnt = nbr_count<DIM>(g, i, j, k);
+    // slot of the node itself = number of valid neighbours that precede it
+    const int bx = (i > 0), by = DIM == 3 ? (j > 0) : 0, bp = (k > 0);
+    const int cx = 1 + (i > 0) + (i < g.NX - 1);
+    const int cy = DIM == 3 ? 1 + (j > 0) + (j < g.NY - 1) : 1;
+    const int self = bp * cx * cy + by * cx + bx;
+    const long long base = (long long)NC * NC * nbr_start[n];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const double dv = nz[base + (long long)c * NC * cnt + self * NC + c];
+      if (diag) diag[n * NC + c] = dv;
+      v[0] += fabs(dv);
+    }
+  }
+  block_partials_finish<1>(v, partials, st, FIN_PLAIN, sm);
+}
+
+// Ferrite apply!(K, f, ch) for homogeneous constraints: zero prescribed rows and columns, put
+// m = mean|diag K| on their diagonal.  `fixed` here is indexed by global lexicographic node.
+template <int NC>
+__global__ void k_csr_apply_bc(long long nrows, const int* __restrict__ rowptr, const int* __restrict__ col,
+                               double* __restrict__ nz, const unsigned char* __restrict__ fixed, const CGState* st,
+                               double inv_n) {
+  const double m = st->sums[0] * inv_n;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < nrows;
+       r += (long long)gridDim.x * blockDim.x) {
+    const bool rf = (fixed[r / NC] >> (r % NC)) & 1;
+    for (int p = rowptr[r]; p < rowptr[r + 1]; ++p) {
+      const int c = col[p];
+      const bool cf = (fixed[c / NC] >> (c % NC)) & 1;
+      if (rf || cf) nz[p] = (c == r) ? m : 0.0;
+    }
+  }
+}
+
+// y = K x, CSR, LANES lanes cooperate on one row; optional fused dot x.y
+template <int LANES, bool DOT>
+__global__ void __launch_bounds__(kBlock) k_spmv(long long nrows, const int* __restrict__ rowptr,
+                                                 const int* __restrict__ col, const double* __restrict__ nz,
+                                                 const double* __restrict__ x, double* __restrict__ y,
+                                                 double* partials, CGState* st, int fin) {
+  __shared__ double sm[32];
+  if (DOT && st->done) return;
+  const int lane = threadIdx.x % LANES;
+  const long long rows_per_pass = (long long)gridDim.x * (blockDim.x / LANES);
+  double dot = 0.0;
+  for (long long r0 = (long long)blockIdx.x * (blockDim.x / LANES); r0 < nrows; r0 += rows_per_pass) {
+    const long long r = r0 + threadIdx.x / LANES;
+    double acc = 0.0;
+    if (r < nrows) {
+      const int b = rowptr[r], e = rowptr[r + 1];
+      for (int p = b + lane; p < e; p += LANES) acc = fma(nz[p], x[col[p]], acc);
+    }
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, LANES);
+    if (lane == 0 && r < nrows) {
+      y[r] = acc;
+      if (DOT) dot = fma(x[r], acc, dot);
+    }
+  }
+  if (DOT) {
+    const double v[1] = {dot};
+    block_partials_finish<1>(v, partials, st, fin, sm);
+  }
+}
+
+}  // namespace topopt

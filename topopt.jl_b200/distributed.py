@@ -1,0 +1,52 @@
+"""Multi-GPU plumbing: one process per GPU, z-slab (last-axis) partition.  torch.distributed is
+used only to ship the NCCL unique id and for barriers; the data path (halo exchange, dot-product
+allreduce) runs inside libtopopt_cuda over its own NCCL communicator."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _lib
+
+
+class SlabComm:
+    def __init__(self, rank, world, nccl_id):
+        self.rank, self.world, self.nccl_id = rank, world, nccl_id
+
+
+def slab_ranges(nlayers, world):
+    """element layers [e0, e1) and owned node planes [k0, k1) per rank (the upper rank owns a
+    shared plane; the last rank also owns the top plane)."""
+    out = []
+    for r in range(world):
+        e0, e1 = r * nlayers // world, (r + 1) * nlayers // world
+        k1 = nlayers + 1 if r == world - 1 else e1
+        out.append(((e0, e1), (e0, k1)))
+    return out
+
+
+def init_from_env(backend=None):
+    """Under torchrun: initialise torch.distributed, broadcast rank 0's ncclUniqueId, return
+    (SlabComm | None, local device ordinal)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1:
+        return None, local
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend)
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        _lib.check(_lib.load().topopt_nccl_unique_id(C.cast(buf, C.c_void_p)))
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0)
+    return SlabComm(rank, world, bytes(t.cpu().tolist())), local

@@ -1,0 +1,252 @@
+"""Host-side mirror of src/FEA: ``FEASolver(Solver, problem; ...)`` returning a
+``GenericFEASolver`` whose call runs the CG solve on the GPU through the C ABI.
+
+Reference: src/FEA/solvers_api.jl:44-66 (solver types), :86-123 (GenericFEASolver fields),
+:285-374 (call operator), :468-574,599-603 (FEASolver factory and defaults),
+src/FEA/convergence_criteria.jl:13-45, src/Utilities/penalties.jl:30-54.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+# ---- penalties (src/Utilities/penalties.jl) ------------------------------------------------
+class PowerPenaltyFun:
+    kind = _lib.PENALTY_POWER
+
+    def __init__(self, p):
+        self.p = float(p)
+
+
+class RationalPenaltyFun(PowerPenaltyFun):
+    kind = _lib.PENALTY_RATIONAL
+
+
+class SinhPenaltyFun(PowerPenaltyFun):
+    kind = _lib.PENALTY_SINH
+
+
+# ---- convergence criteria (src/FEA/convergence_criteria.jl) -----------------------------------
+class DefaultCriteria:
+    code = _lib.CRITERIA_DEFAULT
+
+
+class EnergyCriteria:
+    code = _lib.CRITERIA_ENERGY
+
+
+# ---- solver types selectable through FEASolver(...) (solvers_api.jl:44-66) ---------------------
+class AbstractLinearSolver:
+    pass
+
+
+class CUDAMatrixFreeSolver(AbstractLinearSolver):
+    """GPU counterpart of CGMatrixFreeSolver."""
+
+    op = _lib.OP_MATRIX_FREE
+
+
+class CUDAAssemblySolver(AbstractLinearSolver):
+    """GPU counterpart of CGAssemblySolver (element-gathered CSR + SpMV)."""
+
+    op = _lib.OP_ASSEMBLED
+
+
+class PseudoDensities:
+    """src/TopOpt.jl:30-76 value type; only ``.x`` matters at this boundary."""
+
+    def __init__(self, x):
+        self.x = np.ascontiguousarray(x, dtype=np.float64)
+
+
+def _x(v):
+    return v.x if isinstance(v, PseudoDensities) else np.ascontiguousarray(v, dtype=np.float64)
+
+
+class GenericFEASolver:
+    """Same public fields as the reference struct (solvers_api.jl:100-122) that the objective
+    functions and filters read: problem, u, lhs, rhs, vars, penalty, xmin, cg_max_iter, abstol,
+    preconditioner, conv.  The device handle replaces globalinfo/elementinfo."""
+
+    def __init__(self, solver_type, problem, xmin, penalty, abstol, cg_max_iter, preconditioner, conv, reltol, device, comm, check_every):
+        self.solver_type = solver_type
+        self.problem = problem
+        self.xmin = float(xmin)
+        self.penalty = penalty
+        self.prev_penalty = penalty
+        self.abstol = float(abstol)
+        self.reltol = float(reltol)
+        self.cg_max_iter = int(cg_max_iter)
+        self.preconditioner = preconditioner
+        self.preconditioner_initialized = False
+        self.conv = conv
+        self.check_every = int(check_every)
+        self.u = np.zeros(problem.ndof)
+        self.lhs = np.zeros(problem.ndof)
+        self.rhs = np.zeros(problem.ndof)
+        self.vars = np.ones(problem.nel)
+        self.last_result = None
+        self._lib = _lib.load()
+        self._handle = C.c_void_p()
+        rank, world, uid = (0, 1, None) if comm is None else (comm.rank, comm.world, comm.nccl_id)
+        self.rank, self.world = rank, world
+        d = _lib.Desc()
+        d.dim, d.ncomp = problem.dim, problem.ncomp
+        d.nels = _lib.nels3(problem.nels)
+        d.sizes = (C.c_double * 3)(*([*problem.sizes] + [1.0] * (3 - problem.dim)))
+        Ke = np.ascontiguousarray(problem.Ke.T, dtype=np.float64)  # column-major for the ABI
+        pres, pres_p = _lib.i64(problem.prescribed_dofs)
+        fl = np.ascontiguousarray(problem.fixedload, dtype=np.float64)
+        d.Ke = Ke.ctypes.data_as(_lib.c_dp)
+        d.prescribed_dofs = pres_p
+        d.n_prescribed = pres.shape[0]
+        d.fixedload = fl.ctypes.data_as(_lib.c_dp)
+        d.cellvolumes = None
+        d.cell_dofs = None
+        d.fixed_diag = 0.0
+        d.device = int(device)
+        d.rank, d.world = rank, world
+        self._uid = uid
+        d.nccl_unique_id = C.cast(C.c_char_p(uid), C.c_void_p) if uid is not None else None
+        _lib.check(self._lib.topopt_create(C.byref(d), C.byref(self._handle)))
+
+    # -- lifetime ------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self._lib.topopt_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._handle
+
+    def _check(self, rc):
+        _lib.check(rc, self._handle)
+
+    # -- options -------------------------------------------------------------------------------
+    def cg_opts(self, **over):
+        o = _lib.CGOpts()
+        o.abstol = over.get("abstol", self.abstol)
+        o.reltol = over.get("reltol", self.reltol)
+        o.maxiter = over.get("maxiter", self.cg_max_iter)
+        o.op = self.solver_type.op
+        o.precond = _lib.PRECOND_NONE if self.preconditioner in (None, "identity") else _lib.PRECOND_JACOBI
+        o.criteria = self.conv.code
+        o.check_every = over.get("check_every", self.check_every)
+        return o
+
+    def set_density(self, x=None):
+        """solver.vars .= x and the penalised stiffness on the device (compliance.jl:65)."""
+        if x is not None:
+            self.vars = _x(x)
+        self._check(
+            self._lib.topopt_set_density(self._handle, _lib.ptr(self.vars), self.penalty.kind, self.penalty.p, self.xmin, 1)
+        )
+
+    # -- the call operator (solvers_api.jl:285-374) -----------------------------------------------
+    def __call__(self, assemble_f=True, rhs=None, lhs=None, download=True):
+        """solver(): upload vars, CG solve, write solver.u (or ``lhs`` for a caller-supplied rhs).
+        A 2-D ``rhs`` solves every column with a zero initial guess (solvers_api.jl:294-350)."""
+        self.set_density()
+        if not self.preconditioner_initialized and self.preconditioner not in (None, "identity"):
+            # UpdatePreconditioner! runs once per solver lifetime (solvers_api.jl:187-192)
+            self._check(self._lib.topopt_set_jacobi(self._handle, None))
+            self.preconditioner_initialized = True
+        opts = self.cg_opts()
+        res = _lib.CGResult()
+        if rhs is not None and np.ndim(rhs) == 2:
+            rhs = np.asarray(rhs, dtype=np.float64)
+            out = np.zeros_like(rhs) if lhs is None else lhs
+            for j in range(rhs.shape[1]):
+                col = np.ascontiguousarray(rhs[:, j])
+                sol = np.zeros(self.problem.ndof)
+                self._check(self._lib.topopt_solve(self._handle, _lib.ptr(col), _lib.ptr(sol), C.byref(opts), C.byref(res)))
+                out[:, j] = sol
+            self.last_result = res
+            return out
+        if assemble_f and rhs is None:
+            target = self.u
+            self._check(
+                self._lib.topopt_solve(self._handle, None, _lib.ptr(target) if download else None, C.byref(opts), C.byref(res))
+            )
+        else:
+            b = np.ascontiguousarray(self.rhs if rhs is None else rhs, dtype=np.float64)
+            target = self.lhs if lhs is None else lhs
+            self._check(self._lib.topopt_solve(self._handle, _lib.ptr(b), _lib.ptr(target), C.byref(opts), C.byref(res)))
+        self.last_result = res
+        return target
+
+    # -- operator-level access used by the parity tests -------------------------------------------
+    def mul(self, x):
+        """mul!(y, MatrixFreeOperator, x) (matrix_free_operator.jl:66-105)."""
+        y = np.empty(self.problem.ndof)
+        self._check(self._lib.topopt_apply(self._handle, _lib.ptr(np.ascontiguousarray(x, dtype=np.float64)), _lib.ptr(y)))
+        return y
+
+    def assemble(self):
+        """assemble! + apply! (assemble.jl:28-90): returns (nzval in CSC order, f)."""
+        md = self.problem.metadata
+        nz = np.empty(md.nnz)
+        f = np.empty(md.ndof)
+        self._check(self._lib.topopt_assemble(self._handle, _lib.ptr(nz), _lib.ptr(f)))
+        return nz, f
+
+    def spmv(self, x):
+        y = np.empty(self.problem.ndof)
+        self._check(self._lib.topopt_spmv(self._handle, _lib.ptr(np.ascontiguousarray(x, dtype=np.float64)), _lib.ptr(y)))
+        return y
+
+    def stats(self):
+        s = _lib.Stats()
+        self._check(self._lib.topopt_get_stats(self._handle, C.byref(s)))
+        return s
+
+    def reset_stats(self):
+        self._check(self._lib.topopt_reset_stats(self._handle))
+
+    def time_kernel(self, which, reps, filt=None):
+        ms = C.c_double()
+        self._check(self._lib.topopt_time_kernel(self._handle, filt.handle if filt is not None else None, which, reps, C.byref(ms)))
+        return ms.value
+
+
+def getcompliance(solver):
+    """FEA.getcompliance (src/FEA/FEA.jl:40): u'Ku = dot(u, f) for the solved system."""
+    out = C.c_double()
+    solver._check(solver._lib.topopt_dot(solver.handle, None, None, C.byref(out)))
+    return out.value
+
+
+def FEASolver(Solver, problem, *, xmin=1e-3, penalty=None, abstol=1e-7, cg_max_iter=700, preconditioner=None,
+              conv=None, reltol=None, device=0, comm=None, check_every=0):
+    """FEASolver(Solver, problem; xmin, penalty, abstol, cg_max_iter, preconditioner, conv)
+    with the reference's defaults (solvers_api.jl:468-489).  ``reltol`` is IterativeSolvers'
+    sqrt(eps) unless overridden (the reference cannot override it)."""
+    if not (isinstance(Solver, type) and issubclass(Solver, AbstractLinearSolver)):
+        raise TypeError("Solver must be a subtype of AbstractLinearSolver")
+    if not hasattr(Solver, "op"):
+        raise TypeError(f"{Solver.__name__} has no GPU operator; use CUDAMatrixFreeSolver or CUDAAssemblySolver")
+    return GenericFEASolver(
+        Solver,
+        problem,
+        xmin,
+        penalty if penalty is not None else PowerPenaltyFun(1.0),
+        abstol,
+        cg_max_iter,
+        preconditioner,
+        conv if conv is not None else DefaultCriteria(),
+        reltol if reltol is not None else float(np.sqrt(np.finfo(np.float64).eps)),
+        device,
+        comm,
+        check_every,
+    )
