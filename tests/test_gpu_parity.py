@@ -44,10 +44,24 @@ CASES = {
 }
 
 
+def pair(t, name):
+    """(GPU-side problem, oracle problem) on identical inputs.  The element matrix is an INPUT of
+    the drop-in boundary (Julia passes Kes[1]); both sides get the oracle's Ke so that parity is
+    not blurred by the last-bit differences between two quadrature implementations (those are
+    checked separately in tests/test_abi_cpu.py)."""
+    mk, mko = CASES[name]
+    prob, oprob = mk(t), mko()
+    assert np.max(np.abs(prob.Ke - oprob.Ke)) < 1e-14 * np.max(np.abs(oprob.Ke))
+    prob.Ke = oprob.Ke.copy()
+    assert np.array_equal(prob.prescribed_dofs - 1, oprob.prescribed)
+    assert np.array_equal(prob.fixedload, oprob.fixedload)
+    return prob, oprob
+
+
 @pytest.fixture(params=list(CASES))
 def case(request, lib):
-    mk, mko = CASES[request.param]
-    return lib, mk(lib), mko()
+    prob, oprob = pair(lib, request.param)
+    return lib, prob, oprob
 
 
 def make_solver(t, prob, **kw):
@@ -117,7 +131,7 @@ def test_cg_iterates_match_reference_recurrence(case):
         uref, it, res = o.solve_matfree(oprob, E, abstol=0.0, reltol=0.0, maxiter=maxiter)
         assert s.last_result.iters == it == maxiter
         assert abs(s.last_result.residual - res) <= 1e-10 * max(res, 1e-300)
-        assert rel(u, uref) < 1e-9
+        assert rel(u, uref) < (1e-12 if maxiter <= 5 else 1e-7)
         s.close()
 
 
@@ -230,12 +244,13 @@ def test_multi_rhs_and_user_rhs(lib):
 @pytest.mark.parametrize("name", ["halfmbb2d", "cantilever3d", "heat2d", "cantilever3d_sizes"])
 def test_assembled_matrix_and_spmv(lib, name):
     t = lib
-    mk, mko = CASES[name]
-    prob, oprob = mk(t), mko()
+    prob, oprob = pair(t, name)
     rho = rand_rho(prob.nel)
     E = o.get_rho(rho, 3.0, 1e-3)
     s = t.FEASolver(t.CUDAAssemblySolver, prob, penalty=t.PowerPenaltyFun(3.0), abstol=1e-12, reltol=1e-14, cg_max_iter=20000)
-    s.set_density(rho)
+    # bit-exactness needs bit-identical E_e: hand the oracle's E to the device (pow() on the GPU
+    # and in numpy may differ in the last ulp; test_penalties bounds that at 1e-14)
+    s._check(s._lib.topopt_set_stiffness(s.handle, E.ctypes.data, None))
     nz, f = s.assemble()
     cp, rv, nzref, fref = o.assemble(oprob, E)
     colptr, rowval = prob.metadata.csc_pattern()
@@ -259,8 +274,7 @@ def test_assembled_matrix_and_spmv(lib, name):
 @pytest.mark.parametrize("name,rmin", [("cantilever2d", 2.0), ("halfmbb2d", 1.5), ("cantilever3d", 2.0), ("cantilever3d_sizes", 1.8), ("heat2d", 3.3)])
 def test_filters(lib, name, rmin):
     t = lib
-    mk, mko = CASES[name]
-    prob, oprob = mk(t), mko()
+    prob, oprob = pair(t, name)
     s = make_solver(t, prob)
     F, S = t.DensityFilterFun(s, rmin), t.SensFilterFun(s, rmin)
     Fo, So = o.DensityFilter(oprob, rmin), o.SensFilter(oprob, rmin)
@@ -289,8 +303,7 @@ def test_filter_rmin_too_small(lib):
 def test_simp_ten_iterations(lib, name, filt):
     """Design after 10 SIMP iterations within 1e-6 max|d rho| (shared host-side OC update)."""
     t = lib
-    mk, mko = CASES[name]
-    prob, oprob = mk(t), mko()
+    prob, oprob = pair(t, name)
     if oprob.physics == "heat":
         pytest.skip("fused simp_eval covers the compliance objective; thermal loop checked in test_thermal_compliance")
     s = make_solver(t, prob, abstol=1e-11, reltol=1e-14, cg_max_iter=20000, xmin=1e-3)

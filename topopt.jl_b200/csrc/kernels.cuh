@@ -189,7 +189,7 @@ __global__ void k_penalize(long long n, const double* __restrict__ rho, double* 
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) {
     const double x = rho[e];
-    const double a = pen_first ? x : x * (1.0 - xmin) + xmin;  // argument of the penalty
+    const double a = pen_first ? x : __dadd_rn(__dmul_rn(x, 1.0 - xmin), xmin);  // argument of the penalty
     double f, df;
     if (kind == 0) {  // x^p
       f = pow(a, p);
@@ -204,7 +204,8 @@ __global__ void k_penalize(long long n, const double* __restrict__ rho, double* 
       df = p * cosh(p * a) / s;
     }
     if (pen_first) {
-      E[e] = f * (1.0 - xmin) + xmin;
+      // density(var, xmin) = var*(1-xmin) + xmin, two roundings like the Julia expression (no FMA)
+      E[e] = __dadd_rn(__dmul_rn(f, 1.0 - xmin), xmin);
       dE[e] = (1.0 - xmin) * df;
     } else {
       E[e] = f;

@@ -10,8 +10,27 @@ from . import _lib
 
 
 class SlabComm:
-    def __init__(self, rank, world, nccl_id):
-        self.rank, self.world, self.nccl_id = rank, world, nccl_id
+    """rank/world of the slab decomposition.  Every handle needs its own NCCL communicator, hence
+    its own ncclUniqueId: ``fresh_id()`` is a collective call (rank 0 draws, everyone receives)."""
+
+    def __init__(self, rank, world):
+        self.rank, self.world = rank, world
+
+    def fresh_id(self):
+        import torch
+        import torch.distributed as dist
+
+        buf = C.create_string_buffer(128)
+        if self.rank == 0:
+            _lib.check(_lib.load().topopt_nccl_unique_id(C.cast(buf, C.c_void_p)))
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0)
+        return bytes(t.cpu().tolist())
+
+    @property
+    def nccl_id(self):
+        return self.fresh_id()
 
 
 def slab_ranges(nlayers, world):
@@ -43,10 +62,4 @@ def init_from_env(backend=None):
         if backend == "nccl":
             torch.cuda.set_device(local)
         dist.init_process_group(backend=backend)
-    buf = C.create_string_buffer(128)
-    if rank == 0:
-        _lib.check(_lib.load().topopt_nccl_unique_id(C.cast(buf, C.c_void_p)))
-    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
-    t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=dev)
-    dist.broadcast(t, src=0)
-    return SlabComm(rank, world, bytes(t.cpu().tolist())), local
+    return SlabComm(rank, world), local
