@@ -1,0 +1,155 @@
+"""CPU-side checks of the C ABI: the shared library loads without a GPU, exports every symbol
+include/topopt_cuda.h declares, its host entry points (numbering, connectivity, CSC pattern,
+element matrices) agree BIT-EXACTLY with the oracle, and it refuses to compute without a device.
+Also validates the oracle's C port (the cpu_baseline) against the numpy oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import topopt_oracle as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+GRIDS = [((2, 2), 2), ((7, 4), 2), ((160, 40), 2), ((5, 3), 1), ((3, 2, 2), 3), ((6, 4, 5), 3), ((4, 3, 2), 1), ((1, 1), 2), ((1, 1, 1), 3)]
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from topopt_jl_b200 import _lib
+
+    L = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "topopt_cuda.h")).read()
+    declared = set(re.findall(r"\b(topopt_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 28
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/topopt_cuda.h but not exported"
+    assert declared == set(_lib.SIGNATURES), "ctypes binding and header disagree"
+    assert b"sm_100a" in L.topopt_version()
+
+
+@pytest.mark.parametrize("nels,ncomp", GRIDS)
+def test_numbering_bit_exact(lib, nels, ncomp):
+    t = lib
+    md = t.Metadata(len(nels), ncomp, nels)
+    g = o.Grid(nels)
+    omd = o.Metadata(g, ncomp)
+    assert (md.nnodes, md.nel, md.ndof) == (g.nnodes, g.nel, omd.ndof)
+    assert np.array_equal(md.cells, g.cells + 1)
+    assert np.array_equal(md.node_dofs, omd.node_dofs + 1)
+    assert np.array_equal(md.cell_dofs, omd.cell_dofs + 1)
+
+
+@pytest.mark.parametrize("nels,ncomp", [g for g in GRIDS if np.prod(g[0]) < 2000])
+def test_csc_pattern_bit_exact(lib, nels, ncomp):
+    t = lib
+    md = t.Metadata(len(nels), ncomp, nels)
+    colptr, rowval = md.csc_pattern()
+    g = o.Grid(nels)
+    prob = o.Problem(g, o.Metadata(g, ncomp), np.eye(ncomp * 2 ** len(nels)), [], np.zeros(ncomp * g.nnodes), "x")
+    cp, rv = o.csc_pattern(prob)
+    assert md.nnz == rv.shape[0]
+    assert np.array_equal(colptr - 1, cp) and np.array_equal(rowval - 1, rv)
+
+
+def test_config_sizes(lib):
+    """SURVEY 8 config table (ndof, nnz) from the closed forms in the library."""
+    t = lib
+    assert (t.Metadata(2, 2, (600, 200)).ndof, t.Metadata(2, 2, (600, 200)).nnz) == (241602, 4329604)
+    assert (t.Metadata(3, 3, (60, 20, 20)).ndof, t.Metadata(3, 3, (60, 20, 20)).nnz) == (80703, 6061509)
+    m4 = t.Metadata(3, 3, (256, 128, 128))
+    assert (m4.nel, m4.nnodes, m4.ndof, m4.nnz) == (4194304, 4276737, 12830211, 1025865225)
+    assert t.Metadata(2, 1, (1024, 1024)).ndof == 1050625
+
+
+def test_element_matrices_match_oracle(lib):
+    t = lib
+    from topopt_jl_b200 import _lib
+
+    for dim, sizes in ((2, (1.0, 1.0)), (2, (0.5, 2.0)), (3, (1.0, 1.0, 1.0)), (3, (1.0, 0.5, 2.0))):
+        K = t.element_matrix(dim, _lib.PHYSICS_ELASTICITY, sizes, 1.3, 0.3)
+        assert np.max(np.abs(K - o.element_stiffness(dim, sizes, 1.3, 0.3))) < 1e-14
+        assert np.array_equal(K, K.T)
+        H = t.element_matrix(dim, _lib.PHYSICS_HEAT, sizes, 2.0)
+        assert np.max(np.abs(H - o.element_conductivity(dim, sizes, 2.0))) < 1e-14
+
+
+def test_problem_mirror_matches_oracle(lib):
+    t = lib
+    for mk, mko in [
+        (lambda: t.PointLoadCantilever((160, 40)), lambda: o.PointLoadCantilever((160, 40))),
+        (lambda: t.HalfMBB((60, 20)), lambda: o.HalfMBB((60, 20))),
+        (lambda: t.PointLoadCantilever((6, 4, 2), (1.0, 0.5, 2.0)), lambda: o.PointLoadCantilever((6, 4, 2), (1.0, 0.5, 2.0))),
+        (lambda: t.HeatTree((9, 7)), lambda: o.HeatTree((9, 7))),
+    ]:
+        p, q = mk(), mko()
+        assert np.array_equal(p.prescribed_dofs - 1, q.prescribed)
+        assert np.array_equal(p.fixedload, q.fixedload)
+        assert np.allclose(p.cellvolumes, q.cellvolumes)
+        if hasattr(q, "force_dof"):
+            assert p.force_dof == q.force_dof + 1
+    assert t.PointLoadCantilever((160, 40)).force_dof == 161 * 21 * 2  # problems.jl:20
+    assert t.HalfMBB((60, 20)).force_dof == (61 * 20 + 2) * 2  # problems.jl:63
+    with pytest.raises(ValueError):
+        t.PointLoadCantilever((4, 3))
+    with pytest.raises(ValueError):
+        t.HeatConductionProblem((4, 4), Tleft=1.0)
+
+
+def test_invalid_arguments_and_no_cpu_fallback(lib):
+    t = lib
+    from topopt_jl_b200 import _lib
+
+    L = _lib.load()
+    out = (C.c_int64 * 4)()
+    assert L.topopt_sizes(4, 4, _lib.nels3((2, 2)), None, None, None, None) == _lib.ERR_INVALID
+    assert L.topopt_sizes(2, 3, _lib.nels3((2, 2)), None, None, None, None) == _lib.ERR_INVALID
+    assert L.topopt_sizes(2, 2, _lib.nels3((0, 2)), None, None, None, None) == _lib.ERR_INVALID
+    assert b"nels" in L.topopt_last_error(None)
+    import torch
+
+    if not torch.cuda.is_available():
+        # the product path must fail loudly, not fall back to the CPU
+        with pytest.raises(_lib.TopOptCUDAError) as e:
+            t.FEASolver(t.CUDAMatrixFreeSolver, t.HalfMBB((2, 2)))
+        assert e.value.code == _lib.ERR_NO_DEVICE
+    with pytest.raises(TypeError):
+        t.FEASolver(object, t.HalfMBB((2, 2)))
+
+
+def test_product_package_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "topopt.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "topopt_oracle" not in src and "ref_c" not in src and "oracle/" not in src, f
+
+
+@pytest.mark.parametrize("openmp", [False, True])
+def test_c_port_matches_numpy_oracle(openmp):
+    import ref_c
+
+    for nels in ((10, 4, 6), (9, 6)):
+        dim = len(nels)
+        p = o.PointLoadCantilever(nels)
+        R = ref_c.RefProblem(dim, dim, nels, p.Ke, p.prescribed + 1, openmp=openmp)
+        assert np.array_equal(R.cell_dofs(), p.metadata.cell_dofs + 1)
+        rng = np.random.default_rng(5)
+        rho = rng.uniform(0.2, 1, p.nel)
+        E = o.get_rho(rho, 3.0, 1e-3)
+        R.set_density(rho, 3.0, 1e-3)
+        x = rng.standard_normal(p.ndof)
+        yref = o.matfree_mul(p, E, x)
+        assert np.max(np.abs(R.mul(x) - yref)) < 1e-13 * np.max(np.abs(yref))
+        b = p.fixedload.copy()
+        b[p.prescribed] = 0
+        u, it, res = R.cg(b, abstol=0.0, reltol=0.0, maxiter=10)
+        uo, ito, reso = o.solve_matfree(p, E, abstol=0.0, reltol=0.0, maxiter=10)
+        assert it == ito and abs(res - reso) < 1e-11 * reso and np.max(np.abs(u - uo)) < 1e-10 * np.max(np.abs(uo))
+        obj, c, g = R.compliance(uo, rho, 3.0, 1e-3)
+        oo, co, go = o.compliance(p, uo, rho, 3.0, 1e-3)
+        assert abs(obj - oo) < 1e-12 * abs(oo) and np.max(np.abs(g - go)) < 1e-12 * np.max(np.abs(go))
+        assert np.max(np.abs(R.filter(2.0, rho) - o.SensFilter(p, 2.0).pullback(rho))) < 1e-14
+        R.close()
