@@ -11,6 +11,7 @@ LIB = os.path.join(HERE, "libtopopt_cuda.so")
 SOURCES = [os.path.join(HERE, "csrc", "api.cu"), os.path.join(HERE, "csrc", "host_mesh.cpp")]
 DEPS = SOURCES + [
     os.path.join(HERE, "csrc", "kernels.cuh"),
+    os.path.join(HERE, "csrc", "kxu_hex8.cuh"),
     os.path.join(HERE, "csrc", "common.h"),
     os.path.join(ROOT, "include", "topopt_cuda.h"),
 ]

@@ -10,12 +10,14 @@
 #include <cmath>
 #include <mutex>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "common.h"
 #include "kernels.cuh"
+#include "kxu_hex8.cuh"
 
 using namespace topopt;
 
@@ -73,6 +75,9 @@ struct topopt_handle {
   int64_t nloc_el = 0, eoff = 0, nown_el = 0;                     // element vectors
   int64_t plane_dofs = 0;
   double Ke[kMaxKe * kMaxKe];
+  double Kh[48];          // modal coefficients (hex8 elasticity fast path)
+  bool modal_ok = false;  // Ke has the brick/isotropic modal sparsity pattern
+  int kxu_ty = 8, kxu_zc = 16;
   double fixed_diag = 0.0, cellvol = 1.0;
   double sizes[3] = {1, 1, 1};
   // device buffers
@@ -189,6 +194,7 @@ int use_device(topopt_handle* h) {
   if (g_const_owner[h->device & 63] != h->id) {
     CUDA_TRY(h, cudaDeviceSynchronize());
     CUDA_TRY(h, cudaMemcpyToSymbol(cKe, h->Ke, sizeof(double) * h->ks * h->ks, 0, cudaMemcpyHostToDevice));
+    if (h->modal_ok) CUDA_TRY(h, cudaMemcpyToSymbol(cKh, h->Kh, sizeof(double) * 48, 0, cudaMemcpyHostToDevice));
     g_const_owner[h->device & 63] = h->id;
   }
   return TOPOPT_OK;
@@ -282,8 +288,35 @@ int sync(topopt_handle* h) {
 }
 
 // ---- operator application -----------------------------------------------------------------
+constexpr int kMaxPartialBlocks = 16384;
+
+template <int TY, bool DOT>
+int launch_hex8_modal(topopt_handle* h, const double* x, double* y, int fin) {
+  const Geo& g = h->g;
+  const int tilesX = (g.NX + 29) / 30, tilesY = (g.NY + TY - 3) / (TY - 2);
+  int zc = std::max(1, h->kxu_zc);
+  int nchunks = (g.nown + zc - 1) / zc;
+  while ((long long)tilesX * tilesY * nchunks > kMaxPartialBlocks) {
+    zc *= 2;
+    nchunks = (g.nown + zc - 1) / zc;
+  }
+  const int grid = tilesX * tilesY * nchunks;
+  k_apply_hex8_modal<TY, DOT><<<grid, 32 * TY, 0, h->stream>>>(g, x, y, h->d_E, h->d_fixed, h->fixed_diag, tilesX, tilesY, zc,
+                                                                 h->d_partials, h->d_st, fin);
+  h->stats.kernel_launches += 1;
+  return check_launch(h, "k_apply_hex8_modal");
+}
+
 template <bool DOT>
 int launch_apply(topopt_handle* h, const double* x, double* y, int fin) {
+  if (h->dim == 3 && h->nc == 3 && h->modal_ok) {
+    switch (h->kxu_ty) {
+      case 4: return launch_hex8_modal<4, DOT>(h, x, y, fin);
+      case 6: return launch_hex8_modal<6, DOT>(h, x, y, fin);
+      case 12: return launch_hex8_modal<12, DOT>(h, x, y, fin);
+      default: return launch_hex8_modal<8, DOT>(h, x, y, fin);
+    }
+  }
   const int grid = DOT ? kReduceBlocks : grid_for((long long)h->g.S * h->g.nown, kWideGrid);
 #define CALL(D, C) \
   LAUNCH(h, (k_apply<D, C, DOT>), grid, h->g, x, y, h->d_E, h->d_fixed, h->fixed_diag, h->d_partials, h->d_st, fin)
@@ -522,6 +555,49 @@ int topopt_create(const topopt_desc* d, topopt_handle** out) {
   for (int r = 0; r < h->ks; ++r) tr += h->Ke[r * (h->ks + 1)];
   h->fixed_diag = d->fixed_diag > 0 ? d->fixed_diag : tr * (double)h->nel;  // solvers_api.jl:526-527
 
+  // hex8 elasticity fast path: Khat = T' Ke T / 64 must have the 45-entry brick pattern
+  if (h->dim == 3 && h->nc == 3 && !getenv("TOPOPT_KXU_DENSE")) {
+    static const int corner[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+    static const int mode[8][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 1, 0}, {0, 1, 1}, {1, 0, 1}, {1, 1, 1}};
+    double H[8][8];
+    for (int a = 0; a < 8; ++a)
+      for (int m = 0; m < 8; ++m) {
+        double v = 1.0;
+        for (int dd = 0; dd < 3; ++dd)
+          if (mode[m][dd]) v *= corner[a][dd] ? 1.0 : -1.0;
+        H[a][m] = v;
+      }
+    std::vector<double> Kh(24 * 24, 0.0), tmp(24 * 24, 0.0);
+    for (int r = 0; r < 24; ++r)  // tmp = Ke * T
+      for (int m = 0; m < 8; ++m)
+        for (int c = 0; c < 3; ++c) {
+          double acc = 0.0;
+          for (int a = 0; a < 8; ++a) acc += h->Ke[r + 24 * (3 * a + c)] * H[a][m];
+          tmp[r + 24 * (3 * m + c)] = acc;
+        }
+    double kmax = 0.0;
+    for (int m = 0; m < 8; ++m)  // Kh = T' * tmp / 64
+      for (int c = 0; c < 3; ++c)
+        for (int col = 0; col < 24; ++col) {
+          double acc = 0.0;
+          for (int a = 0; a < 8; ++a) acc += H[a][m] * tmp[(3 * a + c) + 24 * col];
+          Kh[(3 * m + c) + 24 * col] = acc / 64.0;
+          kmax = std::max(kmax, std::fabs(acc / 64.0));
+        }
+    std::vector<char> in_pattern(24 * 24, 0);
+    const ModalEntry* pat = modal_pattern();
+    for (int k = 0; k < 45; ++k) {
+      in_pattern[pat[k].row + 24 * pat[k].col] = 1;
+      h->Kh[k] = Kh[pat[k].row + 24 * pat[k].col];
+    }
+    bool ok = kmax > 0.0;
+    for (int k = 0; k < 24 * 24 && ok; ++k)
+      if (!in_pattern[k] && std::fabs(Kh[k]) > 1e-11 * kmax) ok = false;
+    h->modal_ok = ok;
+    if (const char* e = getenv("TOPOPT_KXU_TY")) h->kxu_ty = atoi(e);
+    if (const char* e = getenv("TOPOPT_KXU_ZC")) h->kxu_zc = atoi(e);
+  }
+
   // slab partition along the last axis
   const int NLg = (int)(h->dim == 3 ? gd.nz : gd.ny);
   const int NPg = NLg + 1;
@@ -603,7 +679,7 @@ int topopt_create(const topopt_desc* d, topopt_handle** out) {
   CCUDA(cudaEventCreate(&h->ev1));
   CCUDA(cudaMallocHost((void**)&h->h_st, sizeof(CGState)));
   CTRY(dev_alloc(h, &h->d_st, 1));
-  CTRY(dev_alloc(h, &h->d_partials, (size_t)kWideGrid * 4));
+  CTRY(dev_alloc(h, &h->d_partials, (size_t)std::max(kWideGrid * 4, kMaxPartialBlocks)));
   CTRY(dev_alloc(h, &h->d_block, h->nloc_nodes));
   CTRY(dev_alloc(h, &h->d_fixed, h->nloc_nodes));
   for (double** v : {&h->d_b, &h->d_fload, &h->d_u, &h->d_r, &h->d_p, &h->d_Ap, &h->d_D, &h->d_rhs, &h->d_lam, &h->d_tmp})
