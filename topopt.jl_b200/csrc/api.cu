@@ -83,7 +83,8 @@ struct topopt_handle {
   // device buffers
   int* d_block = nullptr;
   unsigned char* d_fixed = nullptr;
-  double *d_b = nullptr, *d_fload = nullptr, *d_u = nullptr, *d_r = nullptr, *d_p = nullptr, *d_Ap = nullptr;
+  double *d_b = nullptr, *d_fload = nullptr, *d_u = nullptr, *d_r = nullptr, *d_p = nullptr, *d_p2 = nullptr, *d_Ap = nullptr;
+  bool no_fuse = true;  // fusing p = r + beta p into K.u measured slower (LSU-bound kernel); opt in with TOPOPT_FUSE_P=1
   double *d_D = nullptr, *d_rhs = nullptr, *d_lam = nullptr, *d_tmp = nullptr;
   double *d_E = nullptr, *d_dE = nullptr, *d_rho = nullptr, *d_cell = nullptr, *d_grad = nullptr;
   double *d_full_dof = nullptr, *d_full_el = nullptr, *d_design = nullptr, *d_xf = nullptr, *d_gfull = nullptr;
@@ -290,8 +291,8 @@ int sync(topopt_handle* h) {
 // ---- operator application -----------------------------------------------------------------
 constexpr int kMaxPartialBlocks = 16384;
 
-template <int TY, bool DOT>
-int launch_hex8_modal(topopt_handle* h, const double* x, double* y, int fin) {
+template <int TY, bool DOT, bool FUSEP>
+int launch_hex8_modal(topopt_handle* h, const double* x, double* y, int fin, const double* r, double* pnew) {
   const Geo& g = h->g;
   const int tilesX = (g.NX + 29) / 30, tilesY = (g.NY + TY - 3) / (TY - 2);
   int zc = std::max(1, h->kxu_zc);
@@ -301,22 +302,32 @@ int launch_hex8_modal(topopt_handle* h, const double* x, double* y, int fin) {
     nchunks = (g.nown + zc - 1) / zc;
   }
   const int grid = tilesX * tilesY * nchunks;
-  k_apply_hex8_modal<TY, DOT><<<grid, 32 * TY, 0, h->stream>>>(g, x, y, h->d_E, h->d_fixed, h->fixed_diag, tilesX, tilesY, zc,
-                                                                 h->d_partials, h->d_st, fin);
+  const size_t smem = sizeof(double) * 2 * 12 * TY * 32;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    CUDA_TRY(h, cudaFuncSetAttribute(k_apply_hex8_modal<TY, DOT, FUSEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  k_apply_hex8_modal<TY, DOT, FUSEP><<<grid, 32 * TY, smem, h->stream>>>(g, x, y, h->d_E, h->d_fixed, h->fixed_diag, tilesX, tilesY,
+                                                                        zc, h->d_partials, h->d_st, fin, r, pnew);
   h->stats.kernel_launches += 1;
   return check_launch(h, "k_apply_hex8_modal");
 }
 
+template <bool DOT, bool FUSEP>
+int launch_hex8(topopt_handle* h, const double* x, double* y, int fin, const double* r, double* pnew) {
+  switch (h->kxu_ty) {
+    case 4: return launch_hex8_modal<4, DOT, FUSEP>(h, x, y, fin, r, pnew);
+    case 6: return launch_hex8_modal<6, DOT, FUSEP>(h, x, y, fin, r, pnew);
+    case 10: return launch_hex8_modal<10, DOT, FUSEP>(h, x, y, fin, r, pnew);
+    case 12: return launch_hex8_modal<12, DOT, FUSEP>(h, x, y, fin, r, pnew);
+    default: return launch_hex8_modal<8, DOT, FUSEP>(h, x, y, fin, r, pnew);
+  }
+}
+
 template <bool DOT>
 int launch_apply(topopt_handle* h, const double* x, double* y, int fin) {
-  if (h->dim == 3 && h->nc == 3 && h->modal_ok) {
-    switch (h->kxu_ty) {
-      case 4: return launch_hex8_modal<4, DOT>(h, x, y, fin);
-      case 6: return launch_hex8_modal<6, DOT>(h, x, y, fin);
-      case 12: return launch_hex8_modal<12, DOT>(h, x, y, fin);
-      default: return launch_hex8_modal<8, DOT>(h, x, y, fin);
-    }
-  }
+  if (h->dim == 3 && h->nc == 3 && h->modal_ok) return launch_hex8<DOT, false>(h, x, y, fin, nullptr, nullptr);
   const int grid = DOT ? kReduceBlocks : grid_for((long long)h->g.S * h->g.nown, kWideGrid);
 #define CALL(D, C) \
   LAUNCH(h, (k_apply<D, C, DOT>), grid, h->g, x, y, h->d_E, h->d_fixed, h->fixed_diag, h->d_partials, h->d_st, fin)
@@ -381,13 +392,19 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (h->h_st->done || issued >= maxiter) break;
     const int n = std::min(batch, maxiter - issued);
+    const bool fusep = !assembled && !pre && h->world == 1 && h->dim == 3 && h->nc == 3 && h->modal_ok && !h->no_fuse;
     for (int it = 0; it < n; ++it) {
+      if (fusep) {  // p_new = r + beta p_old formed inside the K.u kernel
+        TRY((launch_hex8<true, true>(h, h->d_p, h->d_Ap, FIN_PAP, h->d_r, h->d_p2)));
+        std::swap(h->d_p, h->d_p2);
+      } else {
       LAUNCH(h, k_update_p, vgrid, h->off, h->nown_dofs, h->d_r, h->d_p, D, h->d_st);
       if (assembled) {
         TRY(launch_spmv<true>(h, h->d_p, h->d_Ap, FIN_PAP));
       } else {
         TRY(exchange_halo(h, h->d_p));
         TRY(launch_apply<true>(h, h->d_p, h->d_Ap, FIN_PAP));
+      }
       }
       if (h->world > 1) {
         TRY(allreduce_sums(h, 1));
@@ -595,6 +612,7 @@ int topopt_create(const topopt_desc* d, topopt_handle** out) {
       if (!in_pattern[k] && std::fabs(Kh[k]) > 1e-11 * kmax) ok = false;
     h->modal_ok = ok;
     if (const char* e = getenv("TOPOPT_KXU_TY")) h->kxu_ty = atoi(e);
+    if (getenv("TOPOPT_FUSE_P")) h->no_fuse = false;
     if (const char* e = getenv("TOPOPT_KXU_ZC")) h->kxu_zc = atoi(e);
   }
 
@@ -682,7 +700,7 @@ int topopt_create(const topopt_desc* d, topopt_handle** out) {
   CTRY(dev_alloc(h, &h->d_partials, (size_t)std::max(kWideGrid * 4, kMaxPartialBlocks)));
   CTRY(dev_alloc(h, &h->d_block, h->nloc_nodes));
   CTRY(dev_alloc(h, &h->d_fixed, h->nloc_nodes));
-  for (double** v : {&h->d_b, &h->d_fload, &h->d_u, &h->d_r, &h->d_p, &h->d_Ap, &h->d_D, &h->d_rhs, &h->d_lam, &h->d_tmp})
+  for (double** v : {&h->d_b, &h->d_fload, &h->d_u, &h->d_r, &h->d_p, &h->d_p2, &h->d_Ap, &h->d_D, &h->d_rhs, &h->d_lam, &h->d_tmp})
     CTRY(dev_alloc(h, v, h->nloc_dofs));
   for (double** v : {&h->d_E, &h->d_dE, &h->d_rho, &h->d_cell, &h->d_grad}) CTRY(dev_alloc(h, v, h->nloc_el));
   CTRY(dev_alloc(h, &h->d_full_dof, h->ndof));
@@ -747,7 +765,7 @@ int topopt_destroy(topopt_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  void* ptrs[] = {h->d_block, h->d_fixed, h->d_b, h->d_fload, h->d_u, h->d_r, h->d_p, h->d_Ap, h->d_D, h->d_rhs, h->d_lam,
+  void* ptrs[] = {h->d_block, h->d_fixed, h->d_b, h->d_fload, h->d_u, h->d_r, h->d_p, h->d_p2, h->d_Ap, h->d_D, h->d_rhs, h->d_lam,
                   h->d_tmp, h->d_E, h->d_dE, h->d_rho, h->d_cell, h->d_grad, h->d_full_dof, h->d_full_el, h->d_design,
                   h->d_xf, h->d_gfull, h->d_partials, h->d_st, h->d_nbr_start, h->d_rowptr, h->d_col, h->d_nz, h->d_fasm};
   for (void* p : ptrs)

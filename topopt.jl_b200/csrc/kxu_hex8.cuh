@@ -43,15 +43,21 @@ inline const ModalEntry* modal_pattern() {
   return p;
 }
 
-template <int TY, bool DOT>
+// FUSEP: x is formed on the fly as p_new = r + beta * p_old (the CG direction update,
+// IterativeSolvers' `u .= r .+ beta .* u`), written to pnew on owned nodes, so that the separate
+// vector pass disappears.  p_old / p_new are distinct buffers (neighbouring CTAs read halo values
+// of p_old while the owner writes p_new).
+template <int TY, bool DOT, bool FUSEP>
 __global__ void __launch_bounds__(32 * TY, (TY <= 4 ? 4 : (TY <= 8 ? 2 : 1)))
     k_apply_hex8_modal(Geo g, const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ E,
                        const unsigned char* __restrict__ fixed, double fixed_diag, int tilesX, int tilesY, int zc,
-                       double* partials, CGState* st, int fin) {
-  __shared__ double sU[6][TY][32];
-  __shared__ double sF[6][TY][32];
+                       double* partials, CGState* st, int fin, const double* __restrict__ rvec, double* __restrict__ pnew) {
+  extern __shared__ double smem_dyn[];
+  // two parity buffers, each [12][TY][32]: rows 0-5 = S/D of the next plane, rows 6-11 = partial node sums
+  double(*sX)[12][TY][32] = reinterpret_cast<double(*)[12][TY][32]>(smem_dyn);
   __shared__ double sm[32];
-  if (DOT && st->done) return;
+  if ((DOT || FUSEP) && st->done) return;
+  const double beta = FUSEP ? st->beta : 0.0;
   const int tid = threadIdx.x;
   const int tx = tid & 31, ty = tid >> 5;
   int b = blockIdx.x;
@@ -69,71 +75,72 @@ __global__ void __launch_bounds__(32 * TY, (TY <= 4 ? 4 : (TY <= 8 ? 2 : 1)))
   const long long ncol = node_ok ? (long long)jn * g.NX + in : 0;
   const long long ecol = elem_ok ? (long long)jn * g.nx + in : 0;
   const unsigned FULL = 0xffffffffu;
-  const double* xp = x + ((long long)(z0 - 1) * g.S + ncol) * 3;   // own node, plane z0-1
+  const long long xs = (long long)g.S * 3;
+  long long noff = ((long long)(z0 - 1) * g.S + ncol) * 3;  // own node, plane z0-1
   const unsigned char* fp = fixed + (long long)(z0 - 1) * g.S + ncol;
   const double* Ep = E + (long long)(z0 - 1) * g.SE + ecol;
-  const long long xs = (long long)g.S * 3;
+
+  auto load_node = [&](long long off, double (&v)[3]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double a = node_ok ? x[off + c] : 0.0;
+      if (FUSEP) a = fma(beta, a, node_ok ? rvec[off + c] : 0.0);
+      v[c] = a;
+    }
+  };
 
   // own node column: masked bottom value, raw bottom value (row mask / dot), flag
   double vb[3], xo[3], carry[3] = {0.0, 0.0, 0.0};
-  unsigned char fo = 0;
+  unsigned char fo = node_ok ? fp[0] : 0;
   double dot = 0.0;
-  {
-    fo = node_ok ? fp[0] : 0;
+  load_node(noff, xo);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      xo[c] = node_ok ? xp[c] : 0.0;
-      vb[c] = (fo & (1 << c)) ? 0.0 : xo[c];
-    }
+  for (int c = 0; c < 3; ++c) vb[c] = (fo & (1 << c)) ? 0.0 : xo[c];
+  // plane z0 -> S/D of the first layer published to buffer 0
+  double rt[3];
+  unsigned char ftf = node_ok ? fp[g.S] : 0;
+  load_node(noff + xs, rt);
+  double vt[3], S0[3], D0[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    vt[c] = (ftf & (1 << c)) ? 0.0 : rt[c];
+    S0[c] = vt[c] + vb[c];
+    D0[c] = vt[c] - vb[c];
+    sX[0][c][ty][tx] = S0[c];
+    sX[0][3 + c][ty][tx] = D0[c];
   }
-  // software prefetch of the next plane
-  double rn[3];
+  double Ee;
+  {
+    const int gl = z0 - 1 + g.p0;
+    Ee = (elem_ok && gl >= 0 && gl < g.NLg) ? Ep[0] : 0.0;
+  }
+  // software prefetch of plane z0+1 / layer z0
+  double rn[3] = {0.0, 0.0, 0.0};
   unsigned char fn = 0;
   double En = 0.0;
-  {
+  noff += xs;
+  fp += g.S;
+  Ep += g.SE;
+  if (z0 < z1) {
     fn = node_ok ? fp[g.S] : 0;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) rn[c] = node_ok ? xp[xs + c] : 0.0;
-    const int gl = z0 - 1 + g.p0;
+    load_node(noff + xs, rn);
+    const int gl = z0 + g.p0;
     En = (elem_ok && gl >= 0 && gl < g.NLg) ? Ep[0] : 0.0;
   }
+  __syncthreads();
 
-  for (int ll = z0 - 1; ll < z1; ++ll) {  // element layer ll touches planes ll (bottom), ll+1 (top)
-    double rt[3], Ee = En;
-    const unsigned char ftf = fn;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) rt[c] = rn[c];
-    // prefetch plane ll+2 / layer ll+1 (always inside the allocation: local planes 0..nown+1)
-    xp += xs;
-    fp += g.S;
-    Ep += g.SE;
-    if (ll + 1 < z1) {
-      fn = node_ok ? fp[g.S] : 0;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) rn[c] = node_ok ? xp[xs + c] : 0.0;
-      const int gl = ll + 1 + g.p0;
-      En = (elem_ok && gl >= 0 && gl < g.NLg) ? Ep[0] : 0.0;
-    }
-    // z stage of the forward Hadamard on the own column only; neighbours receive it
+  int par = 0;
+  for (int ll = z0 - 1; ll < z1; ++ll, par ^= 1) {  // element layer ll touches planes ll (bottom), ll+1 (top)
+    // gather S/D of the three neighbour columns (x+1 by shuffle, y+1 row from shared memory)
     double S[4][3], D[4][3];  // columns: 0 own, 1 x+1, 2 y+1, 3 x+1,y+1
-    double vt[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      vt[c] = (ftf & (1 << c)) ? 0.0 : rt[c];  // bcmatrix: constrained columns are zero
-      S[0][c] = vt[c] + vb[c];
-      D[0][c] = vt[c] - vb[c];
-      sU[c][ty][tx] = S[0][c];
-      sU[3 + c][ty][tx] = D[0][c];
-      S[1][c] = __shfl_down_sync(FULL, S[0][c], 1);
-      D[1][c] = __shfl_down_sync(FULL, D[0][c], 1);
-    }
-    __syncthreads();
-    double H0[3] = {0.0, 0.0, 0.0}, H1[3] = {0.0, 0.0, 0.0};  // node-column sums for mz = 0, 1
-    if (ty < TY - 1) {  // the last row only feeds its S/D to the row below it (warp-uniform branch)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      S[2][c] = sU[c][ty + 1][tx];
-      D[2][c] = sU[3 + c][ty + 1][tx];
+      S[0][c] = S0[c];
+      D[0][c] = D0[c];
+      S[1][c] = __shfl_down_sync(FULL, S0[c], 1);
+      D[1][c] = __shfl_down_sync(FULL, D0[c], 1);
+      S[2][c] = sX[par][c][ty + 1 < TY ? ty + 1 : ty][tx];
+      D[2][c] = sX[par][3 + c][ty + 1 < TY ? ty + 1 : ty][tx];
       S[3][c] = __shfl_down_sync(FULL, S[2][c], 1);
       D[3][c] = __shfl_down_sync(FULL, D[2][c], 1);
     }
@@ -175,6 +182,7 @@ __global__ void __launch_bounds__(32 * TY, (TY <= 4 ? 4 : (TY <= 8 ? 2 : 1)))
     vXYZ[2] = cKh[44] * XYZ[2];
     // inverse Hadamard in y and x; the four corner columns are reduced onto node columns
     // BEFORE the z stage (x by shuffle, y through shared memory), so the z stage runs once per node
+    double H0[3], H1[3];  // node-column sums for mz = 0, 1
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const double g10a = vX[c] + vXY[c], g10b = vX[c] - vXY[c];      // (mx=1,mz=0): oy=1, oy=0
@@ -186,35 +194,62 @@ __global__ void __launch_bounds__(32 * TY, (TY <= 4 ? 4 : (TY <= 8 ? 2 : 1)))
       const double h101 = g01b + g11b, h001 = g01b - g11b;
       H0[c] = h000 + __shfl_up_sync(FULL, h100, 1);
       H1[c] = h001 + __shfl_up_sync(FULL, h101, 1);
-      sF[c][ty][tx] = h010 + __shfl_up_sync(FULL, h110, 1);
-      sF[3 + c][ty][tx] = h011 + __shfl_up_sync(FULL, h111, 1);
+      sX[par][6 + c][ty][tx] = h010 + __shfl_up_sync(FULL, h110, 1);
+      sX[par][9 + c][ty][tx] = h011 + __shfl_up_sync(FULL, h111, 1);
     }
+    // publish S/D of the next layer (plane ll+2) into the other parity buffer, then ONE barrier
+    const double xo_next[3] = {rt[0], rt[1], rt[2]};
+    const unsigned char fo_next = ftf;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      vb[c] = vt[c];
+      rt[c] = rn[c];
+    }
+    ftf = fn;
+    Ee = En;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      vt[c] = (ftf & (1 << c)) ? 0.0 : rt[c];
+      S0[c] = vt[c] + vb[c];
+      D0[c] = vt[c] - vb[c];
+      sX[par ^ 1][c][ty][tx] = S0[c];
+      sX[par ^ 1][3 + c][ty][tx] = D0[c];
+    }
+    // prefetch plane ll+3 / layer ll+2
+    noff += xs;
+    fp += g.S;
+    Ep += g.SE;
+    if (ll + 2 < z1) {
+      fn = node_ok ? fp[g.S] : 0;
+      load_node(noff + xs, rn);
+      const int gl = ll + 2 + g.p0;
+      En = (elem_ok && gl >= 0 && gl < g.NLg) ? Ep[0] : 0.0;
     }
     __syncthreads();
     if (ty >= 1) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        H0[c] += sF[c][ty - 1][tx];
-        H1[c] += sF[3 + c][ty - 1][tx];
+        H0[c] += sX[par][6 + c][ty - 1][tx];
+        H1[c] += sX[par][9 + c][ty - 1][tx];
       }
     }
     if (own && ll >= z0) {
-      double* yp = y + ((long long)ll * g.S + ncol) * 3;
+      const long long yo = ((long long)ll * g.S + ncol) * 3;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         double v = carry[c] + (H0[c] - H1[c]);  // bottom plane of this layer + top of the previous one
         if (fo & (1 << c)) v = fixed_diag * xo[c];
-        yp[c] = v;
+        y[yo + c] = v;
+        if (FUSEP) pnew[yo + c] = xo[c];
         if (DOT) dot = fma(xo[c], v, dot);
       }
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       carry[c] = H0[c] + H1[c];
-      xo[c] = rt[c];
-      vb[c] = vt[c];
+      xo[c] = xo_next[c];
     }
-    fo = ftf;
+    fo = fo_next;
   }
   if (DOT) {
     const double v[1] = {dot};
