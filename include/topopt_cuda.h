@@ -136,6 +136,14 @@ int topopt_element_matrix(int32_t dim, int32_t physics, const double* sizes, dou
  * ranks (any transport), every rank then passes them in topopt_desc.nccl_unique_id. */
 int topopt_nccl_unique_id(void* out128);
 
+/* Peer-memory fast path for world > 1 (all ranks on one NVSwitch node, one process per GPU):
+ * every rank exports a blob (cudaIpc handles of its communication block and direction vector),
+ * the host all-gathers the blobs (any transport) and every rank imports all of them.  Afterwards
+ * the CG loop all-reduces its scalars inside the reduction kernels and the K.u kernel reads halo
+ * planes directly from the neighbours' memory over NVLink; without this call NCCL is used. */
+int topopt_ipc_export(topopt_handle* h, void* out, int64_t* nbytes);
+int topopt_ipc_import(topopt_handle* h, const void* all_blobs, int64_t nbytes_each);
+
 /* ---- handle --------------------------------------------------------------------------- */
 /* FEASolver(Solver, problem; ...) (src/FEA/solvers_api.jl:468-574, 599-603) */
 int topopt_create(const topopt_desc* desc, topopt_handle** out);

@@ -100,6 +100,8 @@ SIGNATURES = {
     "topopt_csc_pattern": (C.c_int, [C.c_int32, C.c_int32, c_ip, c_ip, c_ip]),
     "topopt_element_matrix": (C.c_int, [C.c_int32, C.c_int32, c_dp, C.c_double, C.c_double, C.c_int32, c_dp]),
     "topopt_nccl_unique_id": (C.c_int, [VP]),
+    "topopt_ipc_export": (C.c_int, [VP, VP, c_ip]),
+    "topopt_ipc_import": (C.c_int, [VP, VP, C.c_int64]),
     "topopt_create": (C.c_int, [C.POINTER(Desc), C.POINTER(VP)]),
     "topopt_destroy": (C.c_int, [VP]),
     "topopt_get_stats": (C.c_int, [VP, C.POINTER(Stats)]),

@@ -84,6 +84,14 @@ struct topopt_handle {
   int* d_block = nullptr;
   unsigned char* d_fixed = nullptr;
   double *d_b = nullptr, *d_fload = nullptr, *d_u = nullptr, *d_r = nullptr, *d_p = nullptr, *d_p2 = nullptr, *d_Ap = nullptr;
+  // peer-memory communication (cudaIpc): in-kernel allreduce + direct halo reads
+  PeerBlock* d_peerblock = nullptr;  // this rank's block (IPC-exported)
+  PeerComm* d_peercomm = nullptr;    // device copy of the mapping table
+  void* peer_mapped[3 * kMaxRanks] = {nullptr};
+  const double* peer_p_lo = nullptr;   // lower neighbour's d_p (mapped)
+  const double* peer_p_hi = nullptr;   // upper neighbour's d_p (mapped)
+  bool peer_ready = false;
+  int nown_lower = 0;
   bool no_fuse = true;  // fusing p = r + beta p into K.u measured slower (LSU-bound kernel); opt in with TOPOPT_FUSE_P=1
   double *d_D = nullptr, *d_rhs = nullptr, *d_lam = nullptr, *d_tmp = nullptr;
   double *d_E = nullptr, *d_dE = nullptr, *d_rho = nullptr, *d_cell = nullptr, *d_grad = nullptr;
@@ -291,7 +299,7 @@ int sync(topopt_handle* h) {
 // ---- operator application -----------------------------------------------------------------
 constexpr int kMaxPartialBlocks = 16384;
 
-template <int TY, bool DOT, bool FUSEP>
+template <int TY, bool DOT, bool FUSEP, bool PEER>
 int launch_hex8_modal(topopt_handle* h, const double* x, double* y, int fin, const double* r, double* pnew) {
   const Geo& g = h->g;
   const int tilesX = (g.NX + 29) / 30, tilesY = (g.NY + TY - 3) / (TY - 2);
@@ -305,23 +313,27 @@ int launch_hex8_modal(topopt_handle* h, const double* x, double* y, int fin, con
   const size_t smem = sizeof(double) * 2 * 12 * TY * 32;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
-    CUDA_TRY(h, cudaFuncSetAttribute(k_apply_hex8_modal<TY, DOT, FUSEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_apply_hex8_modal<TY, DOT, FUSEP, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  k_apply_hex8_modal<TY, DOT, FUSEP><<<grid, 32 * TY, smem, h->stream>>>(g, x, y, h->d_E, h->d_fixed, h->fixed_diag, tilesX, tilesY,
-                                                                        zc, h->d_partials, h->d_st, fin, r, pnew);
+  const double* xlo = nullptr;
+  const double* xhi = nullptr;
+  if (PEER) {  // neighbours' boundary planes of the same buffer (d_p), read over NVLink
+    if (h->peer_p_lo) xlo = h->peer_p_lo + (size_t)h->plane_dofs * h->nown_lower;
+    if (h->peer_p_hi) xhi = h->peer_p_hi + (size_t)h->plane_dofs;
+  }
+  k_apply_hex8_modal<TY, DOT, FUSEP, PEER><<<grid, 32 * TY, smem, h->stream>>>(g, x, y, h->d_E, h->d_fixed, h->fixed_diag, tilesX,
+                                                                              tilesY, zc, h->d_partials, h->d_st, fin, r, pnew, xlo, xhi);
   h->stats.kernel_launches += 1;
   return check_launch(h, "k_apply_hex8_modal");
 }
 
-template <bool DOT, bool FUSEP>
+template <bool DOT, bool FUSEP, bool PEER = false>
 int launch_hex8(topopt_handle* h, const double* x, double* y, int fin, const double* r, double* pnew) {
   switch (h->kxu_ty) {
-    case 4: return launch_hex8_modal<4, DOT, FUSEP>(h, x, y, fin, r, pnew);
-    case 6: return launch_hex8_modal<6, DOT, FUSEP>(h, x, y, fin, r, pnew);
-    case 10: return launch_hex8_modal<10, DOT, FUSEP>(h, x, y, fin, r, pnew);
-    case 12: return launch_hex8_modal<12, DOT, FUSEP>(h, x, y, fin, r, pnew);
-    default: return launch_hex8_modal<8, DOT, FUSEP>(h, x, y, fin, r, pnew);
+    case 6: return launch_hex8_modal<6, DOT, FUSEP, PEER>(h, x, y, fin, r, pnew);
+    case 12: return launch_hex8_modal<12, DOT, FUSEP, PEER>(h, x, y, fin, r, pnew);
+    default: return launch_hex8_modal<8, DOT, FUSEP, PEER>(h, x, y, fin, r, pnew);
   }
 }
 
@@ -373,13 +385,16 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
   s.criteria = ignore_convergence ? 0 : o->criteria;
   s.precond = pre ? 1 : 0;
   s.world = h->world;
+  const bool peer = h->world > 1 && h->peer_ready;                       // in-kernel allreduce over peer memory
+  const bool peer_halo = peer && !assembled && h->dim == 3 && h->nc == 3 && h->modal_ok;  // + direct halo reads
+  s.peer = peer ? h->d_peercomm : nullptr;
   CUDA_TRY(h, cudaMemcpyAsync(h->d_st, &s, sizeof(CGState), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
   const double* D = pre ? h->d_D : nullptr;
   const int vgrid = kReduceBlocks;
   LAUNCH(h, k_cg_init, vgrid, h->off, h->nown_dofs, b, h->d_u, h->d_r, h->d_p, D, h->d_partials, h->d_st);
   TRY(check_launch(h, "k_cg_init"));
-  if (h->world > 1) {
+  if (h->world > 1 && !peer) {
     TRY(allreduce_sums(h, 2));
     k_finalize<<<1, 1, 0, h->stream>>>(h->d_st, FIN_INIT);
     h->stats.kernel_launches += 1;
@@ -402,11 +417,17 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
       if (assembled) {
         TRY(launch_spmv<true>(h, h->d_p, h->d_Ap, FIN_PAP));
       } else {
-        TRY(exchange_halo(h, h->d_p));
-        TRY(launch_apply<true>(h, h->d_p, h->d_Ap, FIN_PAP));
+        if (peer_halo) {
+          k_signal_halo<<<1, 1, 0, h->stream>>>(h->d_st);
+          h->stats.kernel_launches += 1;
+          TRY((launch_hex8<true, false, true>(h, h->d_p, h->d_Ap, FIN_PAP, nullptr, nullptr)));
+        } else {
+          TRY(exchange_halo(h, h->d_p));
+          TRY(launch_apply<true>(h, h->d_p, h->d_Ap, FIN_PAP));
+        }
       }
       }
-      if (h->world > 1) {
+      if (h->world > 1 && !peer) {
         TRY(allreduce_sums(h, 1));
         k_finalize<<<1, 1, 0, h->stream>>>(h->d_st, FIN_PAP);
         h->stats.kernel_launches += 1;
@@ -417,7 +438,7 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
       else
         LAUNCH(h, (k_update_xr<false>), vgrid, h->off, h->nown_dofs, h->d_u, h->d_r, h->d_p, h->d_Ap, D, b,
                h->d_partials, h->d_st);
-      if (h->world > 1) {
+      if (h->world > 1 && !peer) {
         TRY(allreduce_sums(h, 4));
         k_finalize<<<1, 1, 0, h->stream>>>(h->d_st, FIN_RR);
         h->stats.kernel_launches += 1;
@@ -441,6 +462,8 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
     res->tol = h->h_st->tol;
     res->solve_ms = ms;
   }
+  if (h->h_st->nonfinite == 2)
+    return fail(h, TOPOPT_ERR_NCCL, "peer-memory wait timed out: a neighbouring rank stopped participating");
   if (h->h_st->nonfinite)
     return fail(h, TOPOPT_ERR_NONFINITE, "CG: NaN or negative energy detected (EnergyCriteria / residual)");
   return TOPOPT_OK;
@@ -507,6 +530,72 @@ int topopt_nccl_unique_id(void* out128) {
   if (r != ncclSuccess) return fail(nullptr, TOPOPT_ERR_NCCL, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r));
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
   std::memcpy(out128, &id, sizeof(id));
+  return TOPOPT_OK;
+}
+
+// ---- peer-memory setup (world > 1, one process per GPU on one NVSwitch node) ---------------------
+// export: [cudaIpcMemHandle_t of the PeerBlock][cudaIpcMemHandle_t of d_p][int32 nown] = 132 bytes
+int topopt_ipc_export(topopt_handle* h, void* out, int64_t* nbytes) {
+  if (!h || !out || !nbytes) return fail(h, TOPOPT_ERR_INVALID, "topopt_ipc_export: NULL argument");
+  TRY(use_device(h));
+  if (!h->d_peerblock) {
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_peerblock, sizeof(PeerBlock)));
+    CUDA_TRY(h, cudaMemset(h->d_peerblock, 0, sizeof(PeerBlock)));
+  }
+  cudaIpcMemHandle_t hb, hp;
+  CUDA_TRY(h, cudaIpcGetMemHandle(&hb, h->d_peerblock));
+  CUDA_TRY(h, cudaIpcGetMemHandle(&hp, h->d_p));
+  char* o = static_cast<char*>(out);
+  std::memcpy(o, &hb, sizeof(hb));
+  std::memcpy(o + sizeof(hb), &hp, sizeof(hp));
+  const int32_t nown = h->g.nown;
+  std::memcpy(o + 2 * sizeof(hb), &nown, sizeof(nown));
+  *nbytes = 2 * sizeof(hb) + sizeof(nown);
+  return TOPOPT_OK;
+}
+
+// import: the export blobs of all ranks, concatenated in rank order (every rank calls this)
+int topopt_ipc_import(topopt_handle* h, const void* all, int64_t nbytes_each) {
+  if (!h || !all) return fail(h, TOPOPT_ERR_INVALID, "topopt_ipc_import: NULL argument");
+  if (h->world < 2 || h->world > kMaxRanks) return fail(h, TOPOPT_ERR_INVALID, "topopt_ipc_import: needs 2..8 ranks");
+  if (nbytes_each != (int64_t)(2 * sizeof(cudaIpcMemHandle_t) + sizeof(int32_t)) || !h->d_peerblock)
+    return fail(h, TOPOPT_ERR_INVALID, "topopt_ipc_import: call topopt_ipc_export first / bad blob size");
+  TRY(use_device(h));
+  PeerComm pc;
+  std::memset(&pc, 0, sizeof(pc));
+  pc.rank = h->rank;
+  pc.world = h->world;
+  const char* a = static_cast<const char*>(all);
+  for (int r = 0; r < h->world; ++r) {
+    const char* blob = a + (size_t)r * nbytes_each;
+    cudaIpcMemHandle_t hb, hp;
+    int32_t nown = 0;
+    std::memcpy(&hb, blob, sizeof(hb));
+    std::memcpy(&hp, blob + sizeof(hb), sizeof(hp));
+    std::memcpy(&nown, blob + 2 * sizeof(hb), sizeof(nown));
+    if (r == h->rank) {
+      pc.block[r] = h->d_peerblock;
+      continue;
+    }
+    void* m = nullptr;
+    CUDA_TRY(h, cudaIpcOpenMemHandle(&m, hb, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_mapped[r] = m;
+    pc.block[r] = static_cast<PeerBlock*>(m);
+    if (r == h->rank - 1 || r == h->rank + 1) {
+      void* mp = nullptr;
+      CUDA_TRY(h, cudaIpcOpenMemHandle(&mp, hp, cudaIpcMemLazyEnablePeerAccess));
+      h->peer_mapped[kMaxRanks + r] = mp;
+      if (r == h->rank - 1) {
+        h->peer_p_lo = static_cast<const double*>(mp);
+        h->nown_lower = nown;
+      } else {
+        h->peer_p_hi = static_cast<const double*>(mp);
+      }
+    }
+  }
+  if (!h->d_peercomm) CUDA_TRY(h, cudaMalloc((void**)&h->d_peercomm, sizeof(PeerComm)));
+  CUDA_TRY(h, cudaMemcpy(h->d_peercomm, &pc, sizeof(pc), cudaMemcpyHostToDevice));
+  h->peer_ready = !getenv("TOPOPT_NO_PEER");
   return TOPOPT_OK;
 }
 
@@ -765,6 +854,10 @@ int topopt_destroy(topopt_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  for (void* m : h->peer_mapped)
+    if (m) cudaIpcCloseMemHandle(m);
+  if (h->d_peerblock) cudaFree(h->d_peerblock);
+  if (h->d_peercomm) cudaFree(h->d_peercomm);
   void* ptrs[] = {h->d_block, h->d_fixed, h->d_b, h->d_fload, h->d_u, h->d_r, h->d_p, h->d_p2, h->d_Ap, h->d_D, h->d_rhs, h->d_lam,
                   h->d_tmp, h->d_E, h->d_dE, h->d_rho, h->d_cell, h->d_grad, h->d_full_dof, h->d_full_el, h->d_design,
                   h->d_xf, h->d_gfull, h->d_partials, h->d_st, h->d_nbr_start, h->d_rowptr, h->d_col, h->d_nz, h->d_fasm};

@@ -23,13 +23,36 @@ struct Geo {
   int nlay;        // owned element layers (local 1..nlay)
 };
 
+constexpr int kMaxRanks = 8;
+
+// Peer-memory communication block (one per rank, in a cudaIpc-shared allocation that every other
+// rank of the node maps).  Used by the in-kernel one-shot allreduce of the CG scalars and by the
+// halo-ready handshake of the K.u kernel: plain stores / loads over NVLink, no NCCL on the
+// per-iteration path.
+struct PeerBlock {
+  double slots[2][kMaxRanks][8];            // [parity][source rank][scalar]
+  unsigned long long flags[2][kMaxRanks];   // sequence number that slot set belongs to
+  unsigned long long halo_flag[2];          // [0]: written by the rank below, [1]: by the rank above
+};
+
+struct PeerComm {
+  PeerBlock* block[kMaxRanks];  // block[r] = rank r's PeerBlock as mapped into this process
+  unsigned long long seq;       // allreduce sequence number (device-maintained, never reset)
+  unsigned long long halo_seq;  // halo handshake sequence number
+  int rank, world;
+  int timeout;                  // set when a spin-wait gave up (peer died): reported as an NCCL-class error
+};
+
 struct CGState {
   double sums[8];   // this rank's reduction results
   double gsums[8];  // after the allreduce (aliases sums when world == 1)
   double res, prev_res, rho, rho_prev, alpha, beta, tol, abstol, reltol, energy, pAp;
   int iters, done, converged, maxiter, criteria, precond, nonfinite, world;
   unsigned int counter;
+  PeerComm* peer;   // non-null: reductions are all-reduced inside the kernel over peer memory
 };
+
+constexpr long long kSpinLimit = 400000000LL;  // ~1 s of polling before a wait is abandoned
 
 constexpr int kMaxKe = 24;
 __constant__ double cKe[kMaxKe * kMaxKe];  // shared element matrix, column-major
@@ -142,6 +165,62 @@ __device__ __forceinline__ void block_partials_finish(const double (&v)[NS], dou
       cg_finalize(st, which);
     }
   }
+  PeerComm* pc = st->peer;
+  if (st->world > 1 && pc != nullptr && which != FIN_NONE && which != FIN_PLAIN) {
+    // one-shot allreduce over peer memory: every rank stores its partial sums into every rank's
+    // slot array, then waits for all contributions and adds them in rank order (bitwise identical
+    // on all ranks).  Parity double-buffering: a rank can be at most one reduction ahead.
+    __shared__ double sh_sums[NS];
+    const unsigned long long seq = pc->seq + 1;
+    const int par = (int)(seq & 1);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < NS; ++k) sh_sums[k] = a[k];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < pc->world) {
+      PeerBlock* dst = pc->block[threadIdx.x];
+#pragma unroll
+      for (int k = 0; k < NS; ++k) dst->slots[par][pc->rank][k] = sh_sums[k];
+      __threadfence_system();
+      *(volatile unsigned long long*)&dst->flags[par][pc->rank] = seq;
+      // wait for rank threadIdx.x's contribution to arrive in my own block
+      volatile unsigned long long* f = &pc->block[pc->rank]->flags[par][threadIdx.x];
+      long long spins = 0;
+      while (*f != seq) {
+        if (++spins > kSpinLimit) {
+          pc->timeout = 1;
+          break;
+        }
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const PeerBlock* mine = pc->block[pc->rank];
+#pragma unroll
+      for (int k = 0; k < NS; ++k) {
+        double g = 0.0;
+        for (int r = 0; r < pc->world; ++r) g += *(volatile const double*)&mine->slots[par][r][k];
+        st->gsums[k] = g;
+      }
+      pc->seq = seq;
+      if (pc->timeout) st->nonfinite = 2;
+      cg_finalize(st, which);
+    }
+  }
+}
+
+// after the direction update: tell both slab neighbours that this rank's boundary planes of p are
+// final for handshake number halo_seq (they read them directly over NVLink inside K.u)
+__global__ void k_signal_halo(CGState* st) {
+  PeerComm* pc = st->peer;
+  if (st->done) return;
+  const unsigned long long seq = pc->halo_seq + 1;
+  __threadfence_system();
+  if (pc->rank + 1 < pc->world) *(volatile unsigned long long*)&pc->block[pc->rank + 1]->halo_flag[0] = seq;
+  if (pc->rank > 0) *(volatile unsigned long long*)&pc->block[pc->rank - 1]->halo_flag[1] = seq;
+  pc->halo_seq = seq;
 }
 
 __global__ void k_finalize(CGState* st, int which) {

@@ -47,11 +47,12 @@ inline const ModalEntry* modal_pattern() {
 // IterativeSolvers' `u .= r .+ beta .* u`), written to pnew on owned nodes, so that the separate
 // vector pass disappears.  p_old / p_new are distinct buffers (neighbouring CTAs read halo values
 // of p_old while the owner writes p_new).
-template <int TY, bool DOT, bool FUSEP>
+template <int TY, bool DOT, bool FUSEP, bool PEER>
 __global__ void __launch_bounds__(32 * TY, (TY <= 4 ? 4 : (TY <= 8 ? 2 : 1)))
     k_apply_hex8_modal(Geo g, const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ E,
                        const unsigned char* __restrict__ fixed, double fixed_diag, int tilesX, int tilesY, int zc,
-                       double* partials, CGState* st, int fin, const double* __restrict__ rvec, double* __restrict__ pnew) {
+                       double* partials, CGState* st, int fin, const double* __restrict__ rvec, double* __restrict__ pnew,
+                       const double* __restrict__ xlo, const double* __restrict__ xhi) {
   extern __shared__ double smem_dyn[];
   // two parity buffers, each [12][TY][32]: rows 0-5 = S/D of the next plane, rows 6-11 = partial node sums
   double(*sX)[12][TY][32] = reinterpret_cast<double(*)[12][TY][32]>(smem_dyn);
@@ -80,10 +81,36 @@ __global__ void __launch_bounds__(32 * TY, (TY <= 4 ? 4 : (TY <= 8 ? 2 : 1)))
   const unsigned char* fp = fixed + (long long)(z0 - 1) * g.S + ncol;
   const double* Ep = E + (long long)(z0 - 1) * g.SE + ecol;
 
+  // Multi-GPU: the ghost planes (local 0 and nown+1) are read straight from the slab neighbours'
+  // memory (xlo = their top owned plane, xhi = their bottom owned plane); CTAs that touch them
+  // first wait for the neighbours' "direction vector final" flag of this iteration.
+  if (PEER && (xlo != nullptr || xhi != nullptr)) {
+    const bool need_lo = xlo != nullptr && z0 == 1, need_hi = xhi != nullptr && z1 == g.nown + 1;
+    if ((need_lo || need_hi) && tid == 0) {
+      PeerComm* pc = st->peer;
+      const unsigned long long want = pc->halo_seq;  // k_signal_halo ran just before this kernel
+      volatile unsigned long long* f = pc->block[pc->rank]->halo_flag;
+      long long spins = 0;
+      while ((need_lo && f[0] < want) || (need_hi && f[1] < want)) {
+        if (++spins > kSpinLimit) {
+          pc->timeout = 1;
+          break;
+        }
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+  }
   auto load_node = [&](long long off, double (&v)[3]) {
+    const double* src = x + off;
+    if (PEER) {
+      if (xlo != nullptr && off < xs) src = xlo + ncol * 3;
+      if (xhi != nullptr && off >= xs * (g.nown + 1)) src = xhi + ncol * 3;
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      double a = node_ok ? x[off + c] : 0.0;
+      // peer planes change between launches and are not L1-coherent: read them through L2
+      double a = node_ok ? (PEER ? __ldcg(src + c) : src[c]) : 0.0;
       if (FUSEP) a = fma(beta, a, node_ok ? rvec[off + c] : 0.0);
       v[c] = a;
     }
@@ -141,8 +168,13 @@ __global__ void __launch_bounds__(32 * TY, (TY <= 4 ? 4 : (TY <= 8 ? 2 : 1)))
       D[1][c] = __shfl_down_sync(FULL, D0[c], 1);
       S[2][c] = sX[par][c][ty + 1 < TY ? ty + 1 : ty][tx];
       D[2][c] = sX[par][3 + c][ty + 1 < TY ? ty + 1 : ty][tx];
+#ifdef TOPOPT_KXU_LDS_CORNER
+      S[3][c] = sX[par][c][ty + 1 < TY ? ty + 1 : ty][tx < 31 ? tx + 1 : tx];
+      D[3][c] = sX[par][3 + c][ty + 1 < TY ? ty + 1 : ty][tx < 31 ? tx + 1 : tx];
+#else
       S[3][c] = __shfl_down_sync(FULL, S[2][c], 1);
       D[3][c] = __shfl_down_sync(FULL, D[2][c], 1);
+#endif
     }
     // x, y stages -> modal coefficients scaled by E_e (the constant mode is never needed)
     double X[3], Y[3], Z[3], XY[3], YZ[3], XZ[3], XYZ[3];

@@ -32,6 +32,17 @@ class SlabComm:
     def nccl_id(self):
         return self.fresh_id()
 
+    def all_gather_bytes(self, blob: bytes) -> bytes:
+        """Concatenation of every rank's equally sized byte string, in rank order (collective)."""
+        import torch
+        import torch.distributed as dist
+
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        mine = torch.tensor(list(blob), dtype=torch.uint8, device=dev)
+        out = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(out, mine)
+        return b"".join(bytes(t.cpu().tolist()) for t in out)
+
 
 def slab_ranges(nlayers, world):
     """element layers [e0, e1) and owned node planes [k0, k1) per rank (the upper rank owns a
