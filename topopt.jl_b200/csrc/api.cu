@@ -77,7 +77,7 @@ struct topopt_handle {
   double Ke[kMaxKe * kMaxKe];
   double Kh[48];          // modal coefficients (hex8 elasticity fast path)
   bool modal_ok = false;  // Ke has the brick/isotropic modal sparsity pattern
-  int kxu_ty = 8, kxu_zc = 16;
+  int kxu_ty = 12, kxu_zc = 16, kxu_waves = 1;
   double fixed_diag = 0.0, cellvol = 1.0;
   double sizes[3] = {1, 1, 1};
   // device buffers
@@ -303,13 +303,13 @@ template <int TY, bool DOT, bool FUSEP, bool PEER>
 int launch_hex8_modal(topopt_handle* h, const double* x, double* y, int fin, const double* r, double* pnew) {
   const Geo& g = h->g;
   const int tilesX = (g.NX + 29) / 30, tilesY = (g.NY + TY - 3) / (TY - 2);
-  int zc = std::max(1, h->kxu_zc);
-  int nchunks = (g.nown + zc - 1) / zc;
-  while ((long long)tilesX * tilesY * nchunks > kMaxPartialBlocks) {
-    zc *= 2;
-    nchunks = (g.nown + zc - 1) / zc;
-  }
-  const int grid = tilesX * tilesY * nchunks;
+  // persistent grid: resident CTAs per SM (register-limited) x 148 SMs, capped by the work
+  const int zc = h->kxu_zc;
+  const int per_sm = TY <= 4 ? 4 : (TY <= 8 ? 2 : 1);
+  int grid = 148 * per_sm * std::max(1, h->kxu_waves);
+  const long long units = (long long)tilesX * tilesY * g.nown;
+  if (grid > units) grid = (int)units;
+  if (grid > kMaxPartialBlocks) grid = kMaxPartialBlocks;
   const size_t smem = sizeof(double) * 2 * 12 * TY * 32;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
@@ -332,8 +332,11 @@ template <bool DOT, bool FUSEP, bool PEER = false>
 int launch_hex8(topopt_handle* h, const double* x, double* y, int fin, const double* r, double* pnew) {
   switch (h->kxu_ty) {
     case 6: return launch_hex8_modal<6, DOT, FUSEP, PEER>(h, x, y, fin, r, pnew);
-    case 12: return launch_hex8_modal<12, DOT, FUSEP, PEER>(h, x, y, fin, r, pnew);
-    default: return launch_hex8_modal<8, DOT, FUSEP, PEER>(h, x, y, fin, r, pnew);
+    case 8: return launch_hex8_modal<8, DOT, FUSEP, PEER>(h, x, y, fin, r, pnew);
+    case 10: return launch_hex8_modal<10, DOT, FUSEP, PEER>(h, x, y, fin, r, pnew);
+    case 14: return launch_hex8_modal<14, DOT, FUSEP, PEER>(h, x, y, fin, r, pnew);
+    case 16: return launch_hex8_modal<16, DOT, FUSEP, PEER>(h, x, y, fin, r, pnew);
+    default: return launch_hex8_modal<12, DOT, FUSEP, PEER>(h, x, y, fin, r, pnew);
   }
 }
 
@@ -703,6 +706,7 @@ int topopt_create(const topopt_desc* d, topopt_handle** out) {
     if (const char* e = getenv("TOPOPT_KXU_TY")) h->kxu_ty = atoi(e);
     if (getenv("TOPOPT_FUSE_P")) h->no_fuse = false;
     if (const char* e = getenv("TOPOPT_KXU_ZC")) h->kxu_zc = atoi(e);
+    if (const char* e = getenv("TOPOPT_KXU_WAVES")) h->kxu_waves = atoi(e);
   }
 
   // slab partition along the last axis

@@ -61,22 +61,33 @@ __global__ void __launch_bounds__(32 * TY, (TY <= 4 ? 4 : (TY <= 8 ? 2 : 1)))
   const double beta = FUSEP ? st->beta : 0.0;
   const int tid = threadIdx.x;
   const int tx = tid & 31, ty = tid >> 5;
-  int b = blockIdx.x;
-  const int bx = b % tilesX;
-  b /= tilesX;
-  const int by = b % tilesY;
-  const int bz = b / tilesY;
+  const unsigned FULL = 0xffffffffu;
+  const long long xs = (long long)g.S * 3;
+  double dot = 0.0;
+  // Persistent CTAs: the (tile, plane) space is linearised and cut into gridDim.x equal ranges,
+  // so every CTA marches the same number of planes (no wave quantisation, and only one redundant
+  // priming layer per segment).  `zc` is unused in this scheme.
+  const long long units = (long long)tilesX * tilesY * g.nown;
+  long long u0 = units * blockIdx.x / gridDim.x;
+  const long long u1 = units * (blockIdx.x + 1) / gridDim.x;
+  (void)zc;
+  while (u0 < u1) {
+  const int tile = (int)(u0 / g.nown);
+  const int zoff = (int)(u0 % g.nown);
+  const int zlen = (int)min((long long)(g.nown - zoff), u1 - u0);
+  u0 += zlen;
+  const int bx = tile % tilesX;
+  const int by = tile / tilesX;
   const int in = bx * 30 - 1 + tx;          // node / element column
   const int jn = by * (TY - 2) - 1 + ty;
-  const int z0 = 1 + bz * zc;               // first owned local plane of this chunk
-  const int z1 = min(z0 + zc, g.nown + 1);  // one past the last
+  const int z0 = 1 + zoff;                  // first owned local plane of this segment
+  const int z1 = z0 + zlen;                 // one past the last
+  __syncthreads();                          // shared buffers are reused across segments
   const bool node_ok = in >= 0 && in < g.NX && jn >= 0 && jn < g.NY;
   const bool own = node_ok && tx >= 1 && tx <= 30 && ty >= 1 && ty <= TY - 2;
   const bool elem_ok = in >= 0 && in < g.nx && jn >= 0 && jn < g.ny && tx < 31 && ty < TY - 1;
   const long long ncol = node_ok ? (long long)jn * g.NX + in : 0;
   const long long ecol = elem_ok ? (long long)jn * g.nx + in : 0;
-  const unsigned FULL = 0xffffffffu;
-  const long long xs = (long long)g.S * 3;
   long long noff = ((long long)(z0 - 1) * g.S + ncol) * 3;  // own node, plane z0-1
   const unsigned char* fp = fixed + (long long)(z0 - 1) * g.S + ncol;
   const double* Ep = E + (long long)(z0 - 1) * g.SE + ecol;
@@ -119,7 +130,6 @@ __global__ void __launch_bounds__(32 * TY, (TY <= 4 ? 4 : (TY <= 8 ? 2 : 1)))
   // own node column: masked bottom value, raw bottom value (row mask / dot), flag
   double vb[3], xo[3], carry[3] = {0.0, 0.0, 0.0};
   unsigned char fo = node_ok ? fp[0] : 0;
-  double dot = 0.0;
   load_node(noff, xo);
 #pragma unroll
   for (int c = 0; c < 3; ++c) vb[c] = (fo & (1 << c)) ? 0.0 : xo[c];
@@ -283,6 +293,7 @@ __global__ void __launch_bounds__(32 * TY, (TY <= 4 ? 4 : (TY <= 8 ? 2 : 1)))
     }
     fo = fo_next;
   }
+  }  // segments
   if (DOT) {
     const double v[1] = {dot};
     block_partials_finish<1>(v, partials, st, fin, sm);
