@@ -466,17 +466,35 @@ __global__ void __launch_bounds__(kBlock) k_cg_init(long long off, long long n, 
   block_partials_finish<2>(v, partials, st, FIN_INIT, sm);
 }
 
-// p = z + beta p   (z = r, or r/D when preconditioned)
+// p = z + beta p   (z = r, or r/D when preconditioned).  4 independent elements per thread and
+// trip keep enough loads in flight to approach the HBM roofline.
 __global__ void __launch_bounds__(kBlock) k_update_p(long long off, long long n, const double* __restrict__ r,
                                                      double* __restrict__ p, const double* __restrict__ D,
                                                      const CGState* __restrict__ st) {
   if (st->done) return;
   const double beta = st->beta;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
-       t += (long long)gridDim.x * blockDim.x) {
-    const long long k = off + t;
-    const double z = D ? r[k] / D[k] : r[k];
-    p[k] = fma(beta, p[k], z);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  r += off;
+  p += off;
+  if (D) D += off;
+  for (; t + 3 * stride < n; t += 4 * stride) {
+    double rv[4], pv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      rv[k] = r[t + k * stride];
+      pv[k] = p[t + k * stride];
+    }
+    if (D) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rv[k] = rv[k] / D[t + k * stride];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) p[t + k * stride] = fma(beta, pv[k], rv[k]);
+  }
+  for (; t < n; t += stride) {
+    const double z = D ? r[t] / D[t] : r[t];
+    p[t] = fma(beta, p[t], z);
   }
 }
 
@@ -491,11 +509,17 @@ __global__ void __launch_bounds__(kBlock) k_update_xr(long long off, long long n
   if (st->done) return;
   const double alpha = st->alpha;
   double v[4] = {0.0, 0.0, 0.0, 0.0};
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
-       t += (long long)gridDim.x * blockDim.x) {
-    const long long k = off + t;
-    const double xv = fma(alpha, p[k], x[k]);
-    const double rv = fma(-alpha, Ap[k], r[k]);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  x += off;
+  r += off;
+  p += off;
+  Ap += off;
+  if (D) D += off;
+  if (ENERGY) b += off;
+  auto body = [&](long long k, double xk, double rk, double pk, double apk) {
+    const double xv = fma(alpha, pk, xk);
+    const double rv = fma(-alpha, apk, rk);
     x[k] = xv;
     r[k] = rv;
     v[0] = fma(rv, rv, v[0]);
@@ -504,7 +528,20 @@ __global__ void __launch_bounds__(kBlock) k_update_xr(long long off, long long n
       v[2] = fma(xv, rv, v[2]);
       v[3] = fma(b[k], xv, v[3]);
     }
+  };
+  for (; t + 3 * stride < n; t += 4 * stride) {
+    double xk[4], rk[4], pk[4], ak[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      xk[k] = x[t + k * stride];
+      rk[k] = r[t + k * stride];
+      pk[k] = p[t + k * stride];
+      ak[k] = Ap[t + k * stride];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) body(t + k * stride, xk[k], rk[k], pk[k], ak[k]);
   }
+  for (; t < n; t += stride) body(t, x[t], r[t], p[t], Ap[t]);
   block_partials_finish<4>(v, partials, st, FIN_RR, sm);
 }
 
