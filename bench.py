@@ -157,7 +157,7 @@ def run_reference(args, nels):
         "e2e": {"value": v, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "kxu_gdofs": info["kxu_gdofs"],
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -264,7 +264,7 @@ def run_native(args, nels):
             "e2e": {"value": args.steps / wall_e2e, "unit": "it/s", "h2d_bytes_per_step": int(st2.h2d_bytes // args.steps),
                     "d2h_bytes_per_step": int(st2.d2h_bytes // args.steps) + 8, "objective": obj_e2e},
             "gpu_launches": launches,
-            "roofline": {"kernel": "k_apply<3,3> (matrix-free K.u, fused p.Ap)", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "k_apply_hex8_modal<12> (matrix-free hex8 K.u)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": kxu_bytes_launch, "ms_per_launch": kxu_ms},
             "kxu_gdofs": prob.ndof / (kxu_ms * 1e-3) / 1e9,
@@ -281,7 +281,7 @@ def run_native(args, nels):
                                         "note": "single-threaded C port of the TopOpt.jl CPU path (the reference hot path has no threading; Julia is not installed)"}
             except Exception as e:  # the baseline must never take the GPU number down with it
                 line["cpu_baseline"] = {"value": None, "unit": "it/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     filt.close()
     solver.close()
     if dist:
@@ -289,7 +289,21 @@ def run_native(args, nels):
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line goes to the real stdout; everything else (NCCL banners, warnings) was
+    rerouted to stderr so that stdout carries exactly one line."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

@@ -20,7 +20,7 @@ def rel(a, b):
 def main():
     comm, local = D.init_from_env()
     assert comm is not None, "run under torchrun with >= 2 ranks"
-    for nels in ((10, 4, 6), (6, 4, 8), (16, 10)):
+    for nels in ((10, 4, 8), (6, 4, 16), (16, 10)):
         prob, oprob = t.PointLoadCantilever(nels), o.PointLoadCantilever(nels)
         prob.Ke = oprob.Ke.copy()
         s = t.FEASolver(t.CUDAMatrixFreeSolver, prob, penalty=t.PowerPenaltyFun(3.0), abstol=1e-12, reltol=1e-14,

@@ -411,18 +411,28 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
     if (h->h_st->done || issued >= maxiter) break;
     const int n = std::min(batch, maxiter - issued);
     const bool fusep = !assembled && !pre && h->world == 1 && h->dim == 3 && h->nc == 3 && h->modal_ok && !h->no_fuse;
+    // TOPOPT_TRACE=1: per-phase device times of the first batch (diagnostic, perturbs the run)
+    static const bool trace = getenv("TOPOPT_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&]() {
+      if (!trace || issued > 0) return;
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, h->stream);
+      tev.push_back(e);
+    };
     for (int it = 0; it < n; ++it) {
+      mark();
       if (fusep) {  // p_new = r + beta p_old formed inside the K.u kernel
         TRY((launch_hex8<true, true>(h, h->d_p, h->d_Ap, FIN_PAP, h->d_r, h->d_p2)));
         std::swap(h->d_p, h->d_p2);
       } else {
-      LAUNCH(h, k_update_p, vgrid, h->off, h->nown_dofs, h->d_r, h->d_p, D, h->d_st);
+      LAUNCH(h, k_update_p, vgrid, h->off, h->nown_dofs, h->d_r, h->d_p, D, h->d_st, peer_halo ? 1 : 0);
       if (assembled) {
         TRY(launch_spmv<true>(h, h->d_p, h->d_Ap, FIN_PAP));
       } else {
         if (peer_halo) {
-          k_signal_halo<<<1, 1, 0, h->stream>>>(h->d_st);
-          h->stats.kernel_launches += 1;
+          mark();
           TRY((launch_hex8<true, false, true>(h, h->d_p, h->d_Ap, FIN_PAP, nullptr, nullptr)));
         } else {
           TRY(exchange_halo(h, h->d_p));
@@ -435,6 +445,7 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
         k_finalize<<<1, 1, 0, h->stream>>>(h->d_st, FIN_PAP);
         h->stats.kernel_launches += 1;
       }
+      mark();
       if (energy)
         LAUNCH(h, (k_update_xr<true>), vgrid, h->off, h->nown_dofs, h->d_u, h->d_r, h->d_p, h->d_Ap, D, b,
                h->d_partials, h->d_st);
@@ -446,6 +457,22 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
         k_finalize<<<1, 1, 0, h->stream>>>(h->d_st, FIN_RR);
         h->stats.kernel_launches += 1;
       }
+    }
+    if (trace && issued == 0 && !tev.empty()) {
+      mark();
+      cudaStreamSynchronize(h->stream);
+      const int per = (int)((tev.size() - 1) / n);
+      std::vector<double> acc(per, 0.0);
+      for (int it = 1; it < n; ++it)  // skip the first iteration
+        for (int k = 0; k < per; ++k) {
+          float ms = 0;
+          cudaEventElapsedTime(&ms, tev[it * per + k], tev[it * per + k + 1]);
+          acc[k] += ms;
+        }
+      fprintf(stderr, "[topopt trace rank %d] phases/iter (us):", h->rank);
+      for (int k = 0; k < per; ++k) fprintf(stderr, " %.1f", 1e3 * acc[k] / std::max(1, n - 1));
+      fprintf(stderr, "\n");
+      for (cudaEvent_t e : tev) cudaEventDestroy(e);
     }
     TRY(check_launch(h, "cg iteration"));
     issued += n;

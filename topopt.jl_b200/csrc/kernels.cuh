@@ -30,8 +30,9 @@ constexpr int kMaxRanks = 8;
 // halo-ready handshake of the K.u kernel: plain stores / loads over NVLink, no NCCL on the
 // per-iteration path.
 struct PeerBlock {
-  double slots[2][kMaxRanks][8];            // [parity][source rank][scalar]
-  unsigned long long flags[2][kMaxRanks];   // sequence number that slot set belongs to
+  // [parity][source rank][scalar] = (value, sequence number): every scalar travels with its own
+  // sequence tag in ONE aligned 16-byte store, so the receiver needs neither a fence nor a flag
+  double2 slots[2][kMaxRanks][8];
   unsigned long long halo_flag[2];          // [0]: written by the rank below, [1]: by the rank above
 };
 
@@ -171,6 +172,7 @@ __device__ __forceinline__ void block_partials_finish(const double (&v)[NS], dou
     // slot array, then waits for all contributions and adds them in rank order (bitwise identical
     // on all ranks).  Parity double-buffering: a rank can be at most one reduction ahead.
     __shared__ double sh_sums[NS];
+    __shared__ double sh_recv[kMaxRanks][NS];
     const unsigned long long seq = pc->seq + 1;
     const int par = (int)(seq & 1);
     if (threadIdx.x == 0) {
@@ -178,30 +180,32 @@ __device__ __forceinline__ void block_partials_finish(const double (&v)[NS], dou
       for (int k = 0; k < NS; ++k) sh_sums[k] = a[k];
     }
     __syncthreads();
-    if ((int)threadIdx.x < pc->world) {
-      PeerBlock* dst = pc->block[threadIdx.x];
-#pragma unroll
-      for (int k = 0; k < NS; ++k) dst->slots[par][pc->rank][k] = sh_sums[k];
-      __threadfence_system();
-      *(volatile unsigned long long*)&dst->flags[par][pc->rank] = seq;
-      // wait for rank threadIdx.x's contribution to arrive in my own block
-      volatile unsigned long long* f = &pc->block[pc->rank]->flags[par][threadIdx.x];
+    const double tag = __longlong_as_double((long long)seq);
+    if ((int)threadIdx.x < pc->world * NS) {
+      // thread (r, k): store scalar k into rank r's slot, then poll rank r's scalar k in my slots
+      const int r = threadIdx.x / NS, k = threadIdx.x % NS;
+      double2* dst = &pc->block[r]->slots[par][pc->rank][k];
+      asm volatile("st.volatile.global.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(sh_sums[k]), "d"(tag) : "memory");
+      const double2* src = &pc->block[pc->rank]->slots[par][r][k];
+      double val, got;
       long long spins = 0;
-      while (*f != seq) {
+      while (true) {
+        asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(val), "=d"(got) : "l"(src) : "memory");
+        if (__double_as_longlong(got) == (long long)seq) break;
         if (++spins > kSpinLimit) {
           pc->timeout = 1;
+          val = 0.0;
           break;
         }
       }
-      __threadfence_system();
+      sh_recv[r][k] = val;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      const PeerBlock* mine = pc->block[pc->rank];
 #pragma unroll
       for (int k = 0; k < NS; ++k) {
         double g = 0.0;
-        for (int r = 0; r < pc->world; ++r) g += *(volatile const double*)&mine->slots[par][r][k];
+        for (int r = 0; r < pc->world; ++r) g += sh_recv[r][k];  // rank order: identical on all ranks
         st->gsums[k] = g;
       }
       pc->seq = seq;
@@ -470,7 +474,7 @@ __global__ void __launch_bounds__(kBlock) k_cg_init(long long off, long long n, 
 // trip keep enough loads in flight to approach the HBM roofline.
 __global__ void __launch_bounds__(kBlock) k_update_p(long long off, long long n, const double* __restrict__ r,
                                                      double* __restrict__ p, const double* __restrict__ D,
-                                                     const CGState* __restrict__ st) {
+                                                     CGState* __restrict__ st, int signal_halo) {
   if (st->done) return;
   const double beta = st->beta;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -495,6 +499,23 @@ __global__ void __launch_bounds__(kBlock) k_update_p(long long off, long long n,
   for (; t < n; t += stride) {
     const double z = D ? r[t] / D[t] : r[t];
     p[t] = fma(beta, p[t], z);
+  }
+  if (signal_halo) {
+    // the last CTA to finish tells both slab neighbours that this rank's p is final for this
+    // iteration (they read its boundary planes over NVLink inside their K.u kernel)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int tk = atomicInc(&st->counter, gridDim.x - 1);
+      if (tk == gridDim.x - 1) {
+        PeerComm* pc = st->peer;
+        const unsigned long long seq = pc->halo_seq + 1;
+        __threadfence_system();
+        if (pc->rank + 1 < pc->world) *(volatile unsigned long long*)&pc->block[pc->rank + 1]->halo_flag[0] = seq;
+        if (pc->rank > 0) *(volatile unsigned long long*)&pc->block[pc->rank - 1]->halo_flag[1] = seq;
+        pc->halo_seq = seq;
+      }
+    }
   }
 }
 

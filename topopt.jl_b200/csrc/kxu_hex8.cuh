@@ -114,14 +114,21 @@ __global__ void __launch_bounds__(32 * TY, (TY <= 4 ? 4 : (TY <= 8 ? 2 : 1)))
   }
   auto load_node = [&](long long off, double (&v)[3]) {
     const double* src = x + off;
+    bool remote = false;  // CTA-uniform: ghost planes live in the neighbours' memory
     if (PEER) {
-      if (xlo != nullptr && off < xs) src = xlo + ncol * 3;
-      if (xhi != nullptr && off >= xs * (g.nown + 1)) src = xhi + ncol * 3;
+      if (xlo != nullptr && off < xs) {
+        src = xlo + ncol * 3;
+        remote = true;
+      }
+      if (xhi != nullptr && off >= xs * (g.nown + 1)) {
+        src = xhi + ncol * 3;
+        remote = true;
+      }
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       // peer planes change between launches and are not L1-coherent: read them through L2
-      double a = node_ok ? (PEER ? __ldcg(src + c) : src[c]) : 0.0;
+      double a = node_ok ? (remote ? __ldcg(src + c) : src[c]) : 0.0;
       if (FUSEP) a = fma(beta, a, node_ok ? rvec[off + c] : 0.0);
       v[c] = a;
     }
