@@ -398,3 +398,68 @@ def test_config3_sized_solve_properties(lib):
     assert np.all(s.u[prob.prescribed_dofs - 1] == 0.0)
     assert np.all(g1 < 0)
     s.close()
+
+
+def test_config1_2d_cantilever_full_size(lib):
+    """BASELINE config 1 (160x40 quad4, DensityFilter rmin=2, p=3) at full size against the oracle:
+    the oracle still solves it in seconds."""
+    t = lib
+    prob, oprob = t.PointLoadCantilever((160, 40)), o.PointLoadCantilever((160, 40))
+    prob.Ke = oprob.Ke.copy()
+    s = make_solver(t, prob, abstol=1e-11, reltol=1e-14, cg_max_iter=50000)
+    F = t.DensityFilterFun(s, 2.0)
+    x = np.full(prob.nel, 0.5)
+    g = np.empty(prob.nel)
+    obj, res = t.simp_eval(s, F, x, g)
+    Fo = o.DensityFilter(oprob, 2.0)
+    xf = Fo(x)
+    u = o.solve_direct(oprob, o.get_rho(xf, 3.0, 1e-3))
+    oo, _, go = o.compliance(oprob, u, xf, 3.0, 1e-3)
+    assert res.converged == 1
+    assert abs(obj - oo) / oo < RTOL_SOLVE and rel(g, Fo.pullback(go)) < RTOL_SOLVE
+    F.close(); s.close()
+
+
+def test_config2_assembled_halfmbb_full_size(lib):
+    """BASELINE config 2 (HalfMBB 600x200, assembled CSR path): pattern size, assembled == matrix-free
+    operator on free rows, CG on the assembled matrix reaches the matrix-free solution, energy balance."""
+    t = lib
+    prob = t.HalfMBB((600, 200))
+    rho = rand_rho(prob.nel)
+    sa = t.FEASolver(t.CUDAAssemblySolver, prob, penalty=t.PowerPenaltyFun(3.0), abstol=1e-9, reltol=0.0, cg_max_iter=100000)
+    sm = make_solver(t, prob, abstol=1e-9, reltol=0.0, cg_max_iter=100000)
+    sa.set_density(rho); sm.set_density(rho)
+    assert prob.metadata.nnz == 4329604 and prob.metadata.ndof == 241602
+    x = np.random.default_rng(2).standard_normal(prob.ndof)
+    x[prob.prescribed_dofs - 1] = 0.0
+    ya, ym = sa.spmv(x), sm.mul(x)
+    free = np.ones(prob.ndof, dtype=bool); free[prob.prescribed_dofs - 1] = False
+    assert rel(ya[free], ym[free]) < 1e-12          # test/FEA/misc.jl:608-660 (fixed rows differ by design)
+    sa.vars = rho; sm.vars = rho
+    ua, um = sa().copy(), sm().copy()
+    assert sa.last_result.converged == 1 and sm.last_result.converged == 1
+    assert rel(ua, um) < 1e-6                       # test/FEA/misc.jl:663-689 uses rtol 1e-3
+    comp = t.ComplianceFun(sm)
+    v = comp(rho)
+    assert abs(v - float(prob.fixedload @ sm.u)) / v < 1e-6
+    sa.close(); sm.close()
+
+
+def test_config5_heat_full_size(lib):
+    """BASELINE config 5 (1024x1024 heat, SensFilter): J == Q.T, lambda == -T (homogeneous BCs),
+    gradient sign, sens-filter pullback keeps a uniform field (size-independent properties)."""
+    t = lib
+    prob = t.HeatTree((1024, 1024))
+    assert prob.ndof == 1050625 and len(prob.prescribed_dofs) == 1025
+    s = make_solver(t, prob, abstol=1e-8, reltol=0.0, cg_max_iter=200000)
+    tc = t.ThermalComplianceFun(s)
+    rho = np.full(prob.nel, 0.4)
+    J, g = tc.value_and_grad(rho)
+    assert s.last_result.converged == 1
+    assert abs(J - float(prob.fixedload @ s.u)) / J < 1e-10   # test_thermal_compliance.jl:101
+    assert np.all(g <= 0) and np.all(s.u[prob.prescribed_dofs - 1] == 0.0)
+    S = t.SensFilterFun(s, 2.0)
+    assert np.max(np.abs(S.pullback(np.full(prob.nel, 3.0)) - 3.0)) < 1e-12
+    gf = S.pullback(g)
+    assert abs(gf.sum() - g.sum()) / abs(g.sum()) < 0.05      # smoothing roughly preserves the mean
+    S.close(); s.close()
