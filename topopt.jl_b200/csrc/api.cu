@@ -92,6 +92,10 @@ struct topopt_handle {
   const double* peer_p_hi = nullptr;   // upper neighbour's d_p (mapped)
   bool peer_ready = false;
   int nown_lower = 0;
+  // CUDA-graph cache for one batch of CG iterations (same kernel arguments every batch)
+  cudaGraphExec_t cg_graph = nullptr;
+  unsigned long long cg_graph_key = 0;
+  bool use_graphs = true;
   bool no_fuse = true;  // fusing p = r + beta p into K.u measured slower (LSU-bound kernel); opt in with TOPOPT_FUSE_P=1
   double *d_D = nullptr, *d_rhs = nullptr, *d_lam = nullptr, *d_tmp = nullptr;
   double *d_E = nullptr, *d_dE = nullptr, *d_rho = nullptr, *d_cell = nullptr, *d_grad = nullptr;
@@ -421,7 +425,7 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
       cudaEventRecord(e, h->stream);
       tev.push_back(e);
     };
-    for (int it = 0; it < n; ++it) {
+    auto one_iteration = [&]() -> int {
       mark();
       if (fusep) {  // p_new = r + beta p_old formed inside the K.u kernel
         TRY((launch_hex8<true, true>(h, h->d_p, h->d_Ap, FIN_PAP, h->d_r, h->d_p2)));
@@ -457,6 +461,53 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
         k_finalize<<<1, 1, 0, h->stream>>>(h->d_st, FIN_RR);
         h->stats.kernel_launches += 1;
       }
+      return TOPOPT_OK;
+    };
+    // Replay a captured graph of n iterations when nothing in the batch depends on host state:
+    // single GPU or the peer-memory path (no NCCL calls inside), no fused pointer swap, no tracing.
+    const bool graphable = h->use_graphs && !trace && !fusep && (h->world == 1 || (peer && (peer_halo || assembled))) && issued > 0;
+    if (graphable) {
+      unsigned long long key = 1469598103934665603ULL;
+      auto mix = [&](unsigned long long v) { key = (key ^ v) * 1099511628211ULL; };
+      mix((unsigned long long)(uintptr_t)b);
+      mix((unsigned long long)(uintptr_t)D);
+      mix((unsigned long long)(uintptr_t)h->d_p);
+      mix((unsigned long long)n);
+      mix((unsigned long long)(energy ? 1 : 0) | (assembled ? 2 : 0) | (peer_halo ? 4 : 0) | (peer ? 8 : 0));
+      if (h->cg_graph == nullptr || h->cg_graph_key != key) {
+        if (h->cg_graph) {
+          cudaGraphExecDestroy(h->cg_graph);
+          h->cg_graph = nullptr;
+        }
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = TOPOPT_OK;
+        for (int it = 0; it < n && rc == TOPOPT_OK; ++it) rc = one_iteration();
+        cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        if (rc != TOPOPT_OK || ce != cudaSuccess || graph == nullptr) {
+          if (graph) cudaGraphDestroy(graph);
+          cudaGetLastError();
+          h->use_graphs = false;  // fall back to plain launches from now on
+          for (int it = 0; it < n; ++it) TRY(one_iteration());
+        } else {
+          ce = cudaGraphInstantiate(&h->cg_graph, graph, 0);
+          cudaGraphDestroy(graph);
+          if (ce != cudaSuccess) {
+            h->cg_graph = nullptr;
+            h->use_graphs = false;
+            cudaGetLastError();
+            for (int it = 0; it < n; ++it) TRY(one_iteration());
+          } else {
+            h->cg_graph_key = key;
+            CUDA_TRY(h, cudaGraphLaunch(h->cg_graph, h->stream));
+          }
+        }
+      } else {
+        CUDA_TRY(h, cudaGraphLaunch(h->cg_graph, h->stream));
+        h->stats.kernel_launches += (long long)n * (assembled || !peer_halo ? 3 : 3);
+      }
+    } else {
+      for (int it = 0; it < n; ++it) TRY(one_iteration());
     }
     if (trace && issued == 0 && !tev.empty()) {
       mark();
@@ -732,6 +783,7 @@ int topopt_create(const topopt_desc* d, topopt_handle** out) {
     h->modal_ok = ok;
     if (const char* e = getenv("TOPOPT_KXU_TY")) h->kxu_ty = atoi(e);
     if (getenv("TOPOPT_FUSE_P")) h->no_fuse = false;
+    if (getenv("TOPOPT_NO_GRAPH")) h->use_graphs = false;
     if (const char* e = getenv("TOPOPT_KXU_ZC")) h->kxu_zc = atoi(e);
     if (const char* e = getenv("TOPOPT_KXU_WAVES")) h->kxu_waves = atoi(e);
   }
@@ -884,6 +936,7 @@ int topopt_destroy(topopt_handle* h) {
   if (!h) return TOPOPT_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->cg_graph) cudaGraphExecDestroy(h->cg_graph);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (void* m : h->peer_mapped)
     if (m) cudaIpcCloseMemHandle(m);
