@@ -126,6 +126,8 @@ struct topopt_filter {
   double* d_nodal = nullptr;
   double* d_in = nullptr;
   double* d_out = nullptr;
+  bool attr_set = false;
+  std::vector<double> h_w;  // host copy of the cone table
 };
 
 namespace {
@@ -552,10 +554,17 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
 
 int run_sens(topopt_handle* h, const double* u, const double* v, double gsign, double* obj_out) {
   CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+  if (h->dim == 3 && h->nc == 3 && h->modal_ok) {
+    if (u == v)
+      LAUNCH(h, (k_sens_hex8_modal<false>), kWideGrid, h->g, u, v, h->d_E, h->d_dE, h->d_cell, h->d_grad, gsign, h->d_partials, h->d_st);
+    else
+      LAUNCH(h, (k_sens_hex8_modal<true>), kWideGrid, h->g, u, v, h->d_E, h->d_dE, h->d_cell, h->d_grad, gsign, h->d_partials, h->d_st);
+  } else {
 #define CALL(D, C) \
   LAUNCH(h, (k_sens<D, C>), kReduceBlocks, h->g, u, v, h->d_E, h->d_dE, h->d_cell, h->d_grad, gsign, h->d_partials, h->d_st)
-  DISPATCH(h, CALL);
+    DISPATCH(h, CALL);
 #undef CALL
+  }
   TRY(check_launch(h, "k_sens"));
   if (h->world > 1)
     NCCL_TRY(h, g_nccl.AllReduce(h->d_st->sums, h->d_st->sums, 1, ncclDouble, ncclSum, h->comm, h->stream));
@@ -580,14 +589,57 @@ int penalize(topopt_handle* h, int kind, double p, double xmin, int pen_first) {
 // ---- filter internals ---------------------------------------------------------------------
 int filter_run(topopt_filter* f, const double* in_dev, double* out_dev, int mode) {
   topopt_handle* h = f->h;
-  const long long nn = (long long)f->fg.NX * f->fg.NY * f->fg.NZ;
-  const long long ne = (long long)f->fg.nx * f->fg.ny * f->fg.nz;
+  const FilterGeo& fg = f->fg;
+  const long long nn = (long long)fg.NX * fg.NY * fg.NZ;
+  const long long ne = (long long)fg.nx * fg.ny * fg.nz;
+  // shared-memory tiled stencil when the tile fits (it always does for rmin of a few elements)
+  const int BY = fg.dim == 3 ? 4 : 8, BZ = fg.dim == 3 ? 2 : 1;
+  const int wx = 2 * fg.R[0], wy = 2 * fg.R[1], wz = fg.dim == 3 ? 2 * fg.R[2] : 1;
+  const size_t smem = sizeof(double) * ((size_t)(32 + wx - 1) * (BY + wy - 1) * (BZ + wz - 1) + (size_t)wx * wy * wz);
+  const bool tiled = smem <= 160 * 1024 && !getenv("TOPOPT_FILTER_UNTILED");
+  if (tiled && !f->attr_set) {
+    CUDA_TRY(h, cudaFuncSetAttribute(k_filter_stencil<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_filter_stencil<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    f->attr_set = true;
+  }
+  auto blocks = [&](int nxo, int nyo, int nzo) { return ((nxo + 31) / 32) * ((nyo + BY - 1) / BY) * ((nzo + BZ - 1) / BZ); };
+  // cubic 3-D windows with R <= 3: fully unrolled kernel with the cone table in constant memory
+  const int Rc = (fg.dim == 3 && fg.R[0] == fg.R[1] && fg.R[1] == fg.R[2] && fg.R[0] <= 3 && !getenv("TOPOPT_FILTER_GENERIC")) ? fg.R[0] : 0;
+  if (Rc) {
+    CUDA_TRY(h, cudaMemcpyToSymbolAsync(cW, f->h_w.data(), sizeof(double) * f->h_w.size(), 0, cudaMemcpyHostToDevice, h->stream));
+    auto blocks3 = [&](int nxo, int nyo, int nzo) { return ((nxo + 31) / 32) * ((nyo + 3) / 4) * ((nzo + 3) / 4); };
+    const bool fwd = mode == TOPOPT_FILTER_FORWARD;
+    if (fwd) LAUNCH(h, k_filter_c2n, grid_for(nn, kWideGrid), fg, in_dev, f->d_nodal);
+    const int nb = fwd ? blocks3(fg.nx, fg.ny, fg.nz) : blocks3(fg.NX, fg.NY, fg.NZ);
+    const double* src = fwd ? f->d_nodal : in_dev;
+    double* dst = fwd ? out_dev : f->d_nodal;
+#define STENCIL3(RR)                                                                                  \
+  if (fwd)                                                                                            \
+    k_filter_stencil3<RR, false><<<nb, 128, 0, h->stream>>>(fg, src, f->d_den, dst);                  \
+  else                                                                                                \
+    k_filter_stencil3<RR, true><<<nb, 128, 0, h->stream>>>(fg, src, f->d_den, dst);
+    if (Rc == 1) { STENCIL3(1) } else if (Rc == 2) { STENCIL3(2) } else { STENCIL3(3) }
+#undef STENCIL3
+    h->stats.kernel_launches += 1;
+    if (!fwd) LAUNCH(h, k_filter_n2c_T, grid_for(ne, kWideGrid), fg, f->d_nodal, out_dev);
+    return check_launch(h, "filter");
+  }
   if (mode == TOPOPT_FILTER_FORWARD) {
-    LAUNCH(h, k_filter_c2n, grid_for(nn, kWideGrid), f->fg, in_dev, f->d_nodal);
-    LAUNCH(h, (k_filter_n2c<0>), grid_for(ne, kWideGrid), f->fg, f->d_w, f->d_nodal, f->d_den, out_dev);
+    LAUNCH(h, k_filter_c2n, grid_for(nn, kWideGrid), fg, in_dev, f->d_nodal);
+    if (tiled) {
+      k_filter_stencil<false><<<blocks(fg.nx, fg.ny, fg.nz), kBlock, smem, h->stream>>>(fg, BY, BZ, f->d_w, f->d_nodal, f->d_den, out_dev);
+      h->stats.kernel_launches += 1;
+    } else {
+      LAUNCH(h, (k_filter_n2c<0>), grid_for(ne, kWideGrid), fg, f->d_w, f->d_nodal, f->d_den, out_dev);
+    }
   } else {
-    LAUNCH(h, k_filter_c2n_T, grid_for(nn, kWideGrid), f->fg, f->d_w, in_dev, f->d_den, f->d_nodal);
-    LAUNCH(h, k_filter_n2c_T, grid_for(ne, kWideGrid), f->fg, f->d_nodal, out_dev);
+    if (tiled) {
+      k_filter_stencil<true><<<blocks(fg.NX, fg.NY, fg.NZ), kBlock, smem, h->stream>>>(fg, BY, BZ, f->d_w, in_dev, f->d_den, f->d_nodal);
+      h->stats.kernel_launches += 1;
+    } else {
+      LAUNCH(h, k_filter_c2n_T, grid_for(nn, kWideGrid), fg, f->d_w, in_dev, f->d_den, f->d_nodal);
+    }
+    LAUNCH(h, k_filter_n2c_T, grid_for(ne, kWideGrid), fg, f->d_nodal, out_dev);
   }
   return check_launch(h, "filter");
 }
@@ -1296,6 +1348,7 @@ int topopt_filter_create(topopt_handle* h, double rmin, topopt_filter** out) {
         w[tx + (size_t)wx * (ty + (size_t)wy * tz)] = wt;
         wsum += wt;
       }
+  f->h_w = w;
   if (wsum == 0.0) {
     delete f;
     return fail(h, TOPOPT_ERR_INVALID,
@@ -1415,14 +1468,9 @@ int topopt_time_kernel(topopt_handle* h, topopt_filter* f, int32_t which, int32_
     }
     case 2:
       CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
-      for (int r = 0; r < reps; ++r) {
-#define CALL(D, C) \
-  LAUNCH(h, (k_sens<D, C>), kReduceBlocks, h->g, h->d_u, h->d_u, h->d_E, h->d_dE, h->d_cell, h->d_grad, -1.0, h->d_partials, h->d_st)
-        DISPATCH(h, CALL);
-#undef CALL
-      }
-      CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
-      break;
+      for (int r = 0; r < reps; ++r) TRY(run_sens(h, h->d_u, h->d_u, -1.0, nullptr));
+      *ms_out = h->stats.last_sens_ms;
+      return TOPOPT_OK;
     case 3:
       if (!f) return fail(h, TOPOPT_ERR_INVALID, "topopt_time_kernel: filter needed");
       CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));

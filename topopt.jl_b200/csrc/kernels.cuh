@@ -710,6 +710,116 @@ __global__ void k_filter_n2c(FilterGeo f, const double* __restrict__ wtab, const
   }
 }
 
+// Shared-memory tiled radius stencil used by both filter directions:
+//   forward   (TRANSPOSE = false): out = cells, in = nodal sums s;  y_i = sum_t w[t] s[i + 1 - R + t] / den_i
+//   transpose (TRANSPOSE = true):  out = nodes, in = cells (d/den); t_n = sum_t w[t] (d/den)[n - R + t]
+// (the cone table is symmetric, w[t] = w[2R-1-t], so both directions index it with t).  A CTA owns a
+// BX x BY x BZ block of outputs and stages the (B + 2R - 1)^dim input tile once.
+template <bool TRANSPOSE>
+__global__ void __launch_bounds__(kBlock) k_filter_stencil(FilterGeo f, int BY, int BZ, const double* __restrict__ wtab,
+                                                           const double* __restrict__ in, const double* __restrict__ den,
+                                                           double* __restrict__ out) {
+  extern __shared__ double tile[];
+  constexpr int BX = 32;
+  const int ox_n = TRANSPOSE ? f.NX : f.nx, oy_n = TRANSPOSE ? f.NY : f.ny, oz_n = TRANSPOSE ? f.NZ : f.nz;  // outputs
+  const int ix_n = TRANSPOSE ? f.nx : f.NX, iy_n = TRANSPOSE ? f.ny : f.NY, iz_n = TRANSPOSE ? f.nz : f.NZ;  // inputs
+  const int wx = 2 * f.R[0], wy = 2 * f.R[1], wz = f.dim == 3 ? 2 * f.R[2] : 1;
+  const int WX = BX + wx - 1, WY = BY + wy - 1, WZ = BZ + wz - 1;
+  double* wsm = tile + (size_t)WX * WY * WZ;  // cone table copy
+  const int tilesX = (ox_n + BX - 1) / BX, tilesY = (oy_n + BY - 1) / BY;
+  int b = blockIdx.x;
+  const int bx = b % tilesX;
+  b /= tilesX;
+  const int by = b % tilesY, bz = b / tilesY;
+  const int o0x = bx * BX, o0y = by * BY, o0z = bz * BZ;
+  const int basex = (TRANSPOSE ? -f.R[0] : 1 - f.R[0]), basey = (TRANSPOSE ? -f.R[1] : 1 - f.R[1]);
+  const int basez = f.dim == 3 ? (TRANSPOSE ? -f.R[2] : 1 - f.R[2]) : 0;
+  const int nt = WX * WY * WZ;
+  for (int k = threadIdx.x; k < nt; k += blockDim.x) {
+    const int tx = k % WX, ty = (k / WX) % WY, tz = k / (WX * WY);
+    const int gx = o0x + basex + tx, gy = o0y + basey + ty, gz = o0z + basez + tz;
+    double v = 0.0;
+    if (gx >= 0 && gx < ix_n && gy >= 0 && gy < iy_n && gz >= 0 && gz < iz_n) {
+      const long long gi = gx + (long long)ix_n * (gy + (long long)iy_n * gz);
+      v = TRANSPOSE ? in[gi] / den[gi] : in[gi];
+    }
+    tile[k] = v;
+  }
+  for (int k = threadIdx.x; k < wx * wy * wz; k += blockDim.x) wsm[k] = wtab[k];
+  __syncthreads();
+  const int lx = threadIdx.x % BX, ly = (threadIdx.x / BX) % BY, lz = threadIdx.x / (BX * BY);
+  const int ox = o0x + lx, oy = o0y + ly, oz = o0z + lz;
+  if (ox >= ox_n || oy >= oy_n || oz >= oz_n) return;
+  double acc = 0.0;
+  for (int tz = 0; tz < wz; ++tz)
+    for (int ty = 0; ty < wy; ++ty) {
+      const double* row = tile + ((size_t)(lz + tz) * WY + (ly + ty)) * WX + lx;
+      const double* wr = wsm + (tz * wy + ty) * wx;
+      for (int tx = 0; tx < wx; ++tx) acc = fma(wr[tx], row[tx], acc);
+    }
+  const long long oi = ox + (long long)ox_n * (oy + (long long)oy_n * oz);
+  out[oi] = TRANSPOSE ? acc : acc / den[oi];
+}
+
+// Specialisation for cubic windows (R equal on all axes, 3-D): the cone table sits in constant
+// memory and every loop is unrolled, so each weight is an immediate constant-bank operand of its
+// DFMA; a thread owns a z-column of 4 outputs and reuses every staged value for up to 4 of them
+// (28 shared-memory reads per output instead of 64 for R = 2).
+__constant__ double cW[216];
+
+template <int R, bool TRANSPOSE>
+__global__ void __launch_bounds__(128) k_filter_stencil3(FilterGeo f, const double* __restrict__ in,
+                                                          const double* __restrict__ den, double* __restrict__ out) {
+  constexpr int BX = 32, BY = 4, BZ = 4, W = 2 * R;
+  constexpr int WX = BX + W - 1, WY = BY + W - 1, WZ = BZ + W - 1;
+  __shared__ double tile[WZ][WY][WX];
+  const int ox_n = TRANSPOSE ? f.NX : f.nx, oy_n = TRANSPOSE ? f.NY : f.ny, oz_n = TRANSPOSE ? f.NZ : f.nz;
+  const int ix_n = TRANSPOSE ? f.nx : f.NX, iy_n = TRANSPOSE ? f.ny : f.NY, iz_n = TRANSPOSE ? f.nz : f.NZ;
+  const int tilesX = (ox_n + BX - 1) / BX, tilesY = (oy_n + BY - 1) / BY;
+  int b = blockIdx.x;
+  const int bx = b % tilesX;
+  b /= tilesX;
+  const int by = b % tilesY, bz = b / tilesY;
+  const int o0x = bx * BX, o0y = by * BY, o0z = bz * BZ;
+  constexpr int base = TRANSPOSE ? -R : 1 - R;
+  for (int k = threadIdx.x; k < WX * WY * WZ; k += blockDim.x) {
+    const int tx = k % WX, ty = (k / WX) % WY, tz = k / (WX * WY);
+    const int gx = o0x + base + tx, gy = o0y + base + ty, gz = o0z + base + tz;
+    double v = 0.0;
+    if (gx >= 0 && gx < ix_n && gy >= 0 && gy < iy_n && gz >= 0 && gz < iz_n) {
+      const long long gi = gx + (long long)ix_n * (gy + (long long)iy_n * gz);
+      v = TRANSPOSE ? in[gi] / den[gi] : in[gi];
+    }
+    tile[tz][ty][tx] = v;
+  }
+  __syncthreads();
+  const int lx = threadIdx.x % BX, ly = threadIdx.x / BX;
+  const int ox = o0x + lx, oy = o0y + ly;
+  if (ox >= ox_n || oy >= oy_n) return;
+  double acc[BZ];
+#pragma unroll
+  for (int k = 0; k < BZ; ++k) acc[k] = 0.0;
+#pragma unroll
+  for (int tz = 0; tz < WZ; ++tz)
+#pragma unroll
+    for (int ty = 0; ty < W; ++ty)
+#pragma unroll
+      for (int tx = 0; tx < W; ++tx) {
+        const double v = tile[tz][ly + ty][lx + tx];
+#pragma unroll
+        for (int k = 0; k < BZ; ++k)
+          if (tz - k >= 0 && tz - k < W) acc[k] = fma(cW[((tz - k) * W + ty) * W + tx], v, acc[k]);
+      }
+#pragma unroll
+  for (int k = 0; k < BZ; ++k) {
+    const int oz = o0z + k;
+    if (oz < oz_n) {
+      const long long oi = ox + (long long)ox_n * (oy + (long long)oy_n * oz);
+      out[oi] = TRANSPOSE ? acc[k] : acc[k] / den[oi];
+    }
+  }
+}
+
 // transpose, stage 2': t_n = sum_i w(n-i) d_i / den_i   (gather over cells around node n)
 __global__ void k_filter_c2n_T(FilterGeo f, const double* __restrict__ wtab, const double* __restrict__ d,
                                const double* __restrict__ den, double* __restrict__ t) {

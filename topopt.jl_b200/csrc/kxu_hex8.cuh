@@ -307,4 +307,107 @@ __global__ void __launch_bounds__(32 * TY, (TY <= 4 ? 4 : (TY <= 8 ? 2 : 1)))
   }
 }
 
+// ---- compliance / sensitivity in the modal basis -------------------------------------------------
+// u_e' Ke v_e = (T'u_e)' Khat (T'v_e): 45 products instead of 576 (compute_element_energy.jl:18-38,
+// thermal_compliance.jl:144-155 for the bilinear form).
+__device__ __forceinline__ void hex8_modal7(const double (&b)[4], const double (&t)[4], double (&m)[7]) {
+  // columns 0:(0,0) 1:(1,0) 2:(0,1) 3:(1,1); b = bottom plane, t = top plane
+  const double s0 = t[0] + b[0], d0 = t[0] - b[0], s1 = t[1] + b[1], d1 = t[1] - b[1];
+  const double s2 = t[2] + b[2], d2 = t[2] - b[2], s3 = t[3] + b[3], d3 = t[3] - b[3];
+  const double ss0 = s1 + s0, ds0 = s1 - s0, ss1 = s3 + s2, ds1 = s3 - s2;
+  const double sd0 = d1 + d0, dd0 = d1 - d0, sd1 = d3 + d2, dd1 = d3 - d2;
+  m[0] = ds1 + ds0;  // x
+  m[1] = ss1 - ss0;  // y
+  m[2] = sd1 + sd0;  // z
+  m[3] = ds1 - ds0;  // xy
+  m[4] = sd1 - sd0;  // yz
+  m[5] = dd1 + dd0;  // xz
+  m[6] = dd1 - dd0;  // xyz
+}
+
+template <bool BILINEAR>
+__global__ void __launch_bounds__(kBlock) k_sens_hex8_modal(Geo g, const double* __restrict__ u, const double* __restrict__ v,
+                                                            const double* __restrict__ E, const double* __restrict__ dE,
+                                                            double* __restrict__ cell, double* __restrict__ grad, double gsign,
+                                                            double* partials, CGState* st) {
+  __shared__ double sm[32];
+  const long long nel = (long long)g.SE * g.nlay;
+  double obj[1] = {0.0};
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nel; t += (long long)gridDim.x * blockDim.x) {
+    const int inl = (int)(t % g.SE);
+    const int ll = (int)(t / g.SE) + 1;
+    const int i = inl % g.nx, j = inl / g.nx;
+    const long long n00 = ((long long)ll * g.S + (long long)j * g.NX + i) * 3;
+    const long long dy = (long long)g.NX * 3, dz = (long long)g.S * 3;
+    double mu[7][3], mv[7][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const double b[4] = {u[n00 + c], u[n00 + 3 + c], u[n00 + dy + c], u[n00 + dy + 3 + c]};
+      const double tp[4] = {u[n00 + dz + c], u[n00 + dz + 3 + c], u[n00 + dz + dy + c], u[n00 + dz + dy + 3 + c]};
+      double m[7];
+      hex8_modal7(b, tp, m);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) mu[k][c] = m[k];
+      if (BILINEAR) {
+        const double b2[4] = {v[n00 + c], v[n00 + 3 + c], v[n00 + dy + c], v[n00 + dy + 3 + c]};
+        const double t2[4] = {v[n00 + dz + c], v[n00 + dz + 3 + c], v[n00 + dz + dy + c], v[n00 + dz + dy + 3 + c]};
+        hex8_modal7(b2, t2, m);
+      }
+#pragma unroll
+      for (int k = 0; k < 7; ++k) mv[k][c] = m[k];
+    }
+    double ce = 0.0;
+    ce = fma(cKh[0] * mv[0][0], mu[0][0], ce);
+    ce = fma(cKh[1] * mv[0][0], mu[1][1], ce);
+    ce = fma(cKh[2] * mv[0][0], mu[2][2], ce);
+    ce = fma(cKh[3] * mv[1][1], mu[0][0], ce);
+    ce = fma(cKh[4] * mv[1][1], mu[1][1], ce);
+    ce = fma(cKh[5] * mv[1][1], mu[2][2], ce);
+    ce = fma(cKh[6] * mv[2][2], mu[0][0], ce);
+    ce = fma(cKh[7] * mv[2][2], mu[1][1], ce);
+    ce = fma(cKh[8] * mv[2][2], mu[2][2], ce);
+    ce = fma(cKh[9] * mv[0][1], mu[0][1], ce);
+    ce = fma(cKh[10] * mv[0][1], mu[1][0], ce);
+    ce = fma(cKh[11] * mv[1][0], mu[0][1], ce);
+    ce = fma(cKh[12] * mv[1][0], mu[1][0], ce);
+    ce = fma(cKh[13] * mv[0][2], mu[0][2], ce);
+    ce = fma(cKh[14] * mv[0][2], mu[2][0], ce);
+    ce = fma(cKh[15] * mv[2][0], mu[0][2], ce);
+    ce = fma(cKh[16] * mv[2][0], mu[2][0], ce);
+    ce = fma(cKh[17] * mv[1][2], mu[1][2], ce);
+    ce = fma(cKh[18] * mv[1][2], mu[2][1], ce);
+    ce = fma(cKh[19] * mv[2][1], mu[1][2], ce);
+    ce = fma(cKh[20] * mv[2][1], mu[2][1], ce);
+    ce = fma(cKh[21] * mv[3][0], mu[3][0], ce);
+    ce = fma(cKh[22] * mv[3][0], mu[4][2], ce);
+    ce = fma(cKh[23] * mv[4][2], mu[3][0], ce);
+    ce = fma(cKh[24] * mv[4][2], mu[4][2], ce);
+    ce = fma(cKh[25] * mv[3][1], mu[3][1], ce);
+    ce = fma(cKh[26] * mv[3][1], mu[5][2], ce);
+    ce = fma(cKh[27] * mv[5][2], mu[3][1], ce);
+    ce = fma(cKh[28] * mv[5][2], mu[5][2], ce);
+    ce = fma(cKh[29] * mv[4][1], mu[4][1], ce);
+    ce = fma(cKh[30] * mv[4][1], mu[5][0], ce);
+    ce = fma(cKh[31] * mv[5][0], mu[4][1], ce);
+    ce = fma(cKh[32] * mv[5][0], mu[5][0], ce);
+    ce = fma(cKh[33] * mv[3][2], mu[3][2], ce);
+    ce = fma(cKh[34] * mv[3][2], mu[4][0], ce);
+    ce = fma(cKh[35] * mv[3][2], mu[5][1], ce);
+    ce = fma(cKh[36] * mv[4][0], mu[3][2], ce);
+    ce = fma(cKh[37] * mv[4][0], mu[4][0], ce);
+    ce = fma(cKh[38] * mv[4][0], mu[5][1], ce);
+    ce = fma(cKh[39] * mv[5][1], mu[3][2], ce);
+    ce = fma(cKh[40] * mv[5][1], mu[4][0], ce);
+    ce = fma(cKh[41] * mv[5][1], mu[5][1], ce);
+    ce = fma(cKh[42] * mv[6][0], mu[6][0], ce);
+    ce = fma(cKh[43] * mv[6][1], mu[6][1], ce);
+    ce = fma(cKh[44] * mv[6][2], mu[6][2], ce);
+    const long long le = (long long)ll * g.SE + inl;
+    if (cell) cell[le] = ce;
+    if (grad) grad[le] = gsign * dE[le] * ce;
+    obj[0] = fma(E[le], ce, obj[0]);
+  }
+  block_partials_finish<1>(obj, partials, st, FIN_PLAIN, sm);
+}
+
 }  // namespace topopt
