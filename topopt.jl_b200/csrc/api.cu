@@ -77,7 +77,7 @@ struct topopt_handle {
   double Ke[kMaxKe * kMaxKe];
   double Kh[48];          // modal coefficients (hex8 elasticity fast path)
   bool modal_ok = false;  // Ke has the brick/isotropic modal sparsity pattern
-  int kxu_ty = 12, kxu_zc = 16, kxu_waves = 1;
+  int kxu_ty = 16, kxu_zc = 16, kxu_waves = 1, kxu_nsync = 1;
   double fixed_diag = 0.0, cellvol = 1.0;
   double sizes[3] = {1, 1, 1};
   // device buffers
@@ -305,7 +305,7 @@ int sync(topopt_handle* h) {
 // ---- operator application -----------------------------------------------------------------
 constexpr int kMaxPartialBlocks = 16384;
 
-template <int TY, bool DOT, bool FUSEP, bool PEER>
+template <int TY, bool DOT, bool FUSEP, bool PEER, bool NSYNC>
 int launch_hex8_modal(topopt_handle* h, const double* x, double* y, int fin, const double* r, double* pnew) {
   const Geo& g = h->g;
   const int tilesX = (g.NX + 29) / 30, tilesY = (g.NY + TY - 3) / (TY - 2);
@@ -319,7 +319,7 @@ int launch_hex8_modal(topopt_handle* h, const double* x, double* y, int fin, con
   const size_t smem = sizeof(double) * 2 * 12 * TY * 32;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
-    CUDA_TRY(h, cudaFuncSetAttribute(k_apply_hex8_modal<TY, DOT, FUSEP, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_apply_hex8_modal<TY, DOT, FUSEP, PEER, NSYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   const double* xlo = nullptr;
@@ -328,7 +328,7 @@ int launch_hex8_modal(topopt_handle* h, const double* x, double* y, int fin, con
     if (h->peer_p_lo) xlo = h->peer_p_lo + (size_t)h->plane_dofs * h->nown_lower;
     if (h->peer_p_hi) xhi = h->peer_p_hi + (size_t)h->plane_dofs;
   }
-  k_apply_hex8_modal<TY, DOT, FUSEP, PEER><<<grid, 32 * TY, smem, h->stream>>>(g, x, y, h->d_E, h->d_fixed, h->fixed_diag, tilesX,
+  k_apply_hex8_modal<TY, DOT, FUSEP, PEER, NSYNC><<<grid, 32 * TY, smem, h->stream>>>(g, x, y, h->d_E, h->d_fixed, h->fixed_diag, tilesX,
                                                                               tilesY, zc, h->d_partials, h->d_st, fin, r, pnew, xlo, xhi);
   h->stats.kernel_launches += 1;
   return check_launch(h, "k_apply_hex8_modal");
@@ -336,14 +336,16 @@ int launch_hex8_modal(topopt_handle* h, const double* x, double* y, int fin, con
 
 template <bool DOT, bool FUSEP, bool PEER = false>
 int launch_hex8(topopt_handle* h, const double* x, double* y, int fin, const double* r, double* pnew) {
-  switch (h->kxu_ty) {
-    case 6: return launch_hex8_modal<6, DOT, FUSEP, PEER>(h, x, y, fin, r, pnew);
-    case 8: return launch_hex8_modal<8, DOT, FUSEP, PEER>(h, x, y, fin, r, pnew);
-    case 10: return launch_hex8_modal<10, DOT, FUSEP, PEER>(h, x, y, fin, r, pnew);
-    case 14: return launch_hex8_modal<14, DOT, FUSEP, PEER>(h, x, y, fin, r, pnew);
-    case 16: return launch_hex8_modal<16, DOT, FUSEP, PEER>(h, x, y, fin, r, pnew);
-    default: return launch_hex8_modal<12, DOT, FUSEP, PEER>(h, x, y, fin, r, pnew);
+  if (h->kxu_nsync) {
+    if (h->kxu_ty == 8) return launch_hex8_modal<8, DOT, FUSEP, PEER, true>(h, x, y, fin, r, pnew);
+    if (h->kxu_ty == 16) return launch_hex8_modal<16, DOT, FUSEP, PEER, true>(h, x, y, fin, r, pnew);
+    if (h->kxu_ty == 14) return launch_hex8_modal<14, DOT, FUSEP, PEER, true>(h, x, y, fin, r, pnew);
+    if (h->kxu_ty == 20) return launch_hex8_modal<20, DOT, FUSEP, PEER, true>(h, x, y, fin, r, pnew);
+    return launch_hex8_modal<12, DOT, FUSEP, PEER, true>(h, x, y, fin, r, pnew);
   }
+  if (h->kxu_ty == 8) return launch_hex8_modal<8, DOT, FUSEP, PEER, false>(h, x, y, fin, r, pnew);
+  if (h->kxu_ty == 16) return launch_hex8_modal<16, DOT, FUSEP, PEER, false>(h, x, y, fin, r, pnew);
+  return launch_hex8_modal<12, DOT, FUSEP, PEER, false>(h, x, y, fin, r, pnew);
 }
 
 template <bool DOT>
@@ -545,6 +547,7 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
     res->tol = h->h_st->tol;
     res->solve_ms = ms;
   }
+  if (h->h_st->nonfinite == 3) return fail(h, TOPOPT_ERR_CUDA, "K.u kernel: intra-CTA neighbour synchronisation timed out");
   if (h->h_st->nonfinite == 2)
     return fail(h, TOPOPT_ERR_NCCL, "peer-memory wait timed out: a neighbouring rank stopped participating");
   if (h->h_st->nonfinite)
@@ -838,6 +841,7 @@ int topopt_create(const topopt_desc* d, topopt_handle** out) {
     if (getenv("TOPOPT_NO_GRAPH")) h->use_graphs = false;
     if (const char* e = getenv("TOPOPT_KXU_ZC")) h->kxu_zc = atoi(e);
     if (const char* e = getenv("TOPOPT_KXU_WAVES")) h->kxu_waves = atoi(e);
+    if (const char* e = getenv("TOPOPT_KXU_NSYNC")) h->kxu_nsync = atoi(e);
   }
 
   // slab partition along the last axis

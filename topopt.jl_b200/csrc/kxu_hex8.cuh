@@ -47,7 +47,7 @@ inline const ModalEntry* modal_pattern() {
 // IterativeSolvers' `u .= r .+ beta .* u`), written to pnew on owned nodes, so that the separate
 // vector pass disappears.  p_old / p_new are distinct buffers (neighbouring CTAs read halo values
 // of p_old while the owner writes p_new).
-template <int TY, bool DOT, bool FUSEP, bool PEER>
+template <int TY, bool DOT, bool FUSEP, bool PEER, bool NSYNC>
 __global__ void __launch_bounds__(32 * TY, (TY <= 4 ? 4 : (TY <= 8 ? 2 : 1)))
     k_apply_hex8_modal(Geo g, const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ E,
                        const unsigned char* __restrict__ fixed, double fixed_diag, int tilesX, int tilesY, int zc,
@@ -57,7 +57,15 @@ __global__ void __launch_bounds__(32 * TY, (TY <= 4 ? 4 : (TY <= 8 ? 2 : 1)))
   // two parity buffers, each [12][TY][32]: rows 0-5 = S/D of the next plane, rows 6-11 = partial node sums
   double(*sX)[12][TY][32] = reinterpret_cast<double(*)[12][TY][32]>(smem_dyn);
   __shared__ double sm[32];
+  // NSYNC: rows synchronise only with their two neighbours (a per-row "published step" counter in
+  // shared memory) instead of a CTA-wide barrier, so warps drift apart and the exchange phase of
+  // one row overlaps the fp64 phase of another.
+  __shared__ int sflag[TY];
+  int it = 0;  // published-step counter, monotonic across segments
   if ((DOT || FUSEP) && st->done) return;
+  if (NSYNC) {
+    if (threadIdx.x < TY) sflag[threadIdx.x] = 0;
+  }
   const double beta = FUSEP ? st->beta : 0.0;
   const int tid = threadIdx.x;
   const int tx = tid & 31, ty = tid >> 5;
@@ -274,7 +282,26 @@ __global__ void __launch_bounds__(32 * TY, (TY <= 4 ? 4 : (TY <= 8 ? 2 : 1)))
       const int gl = ll + 2 + g.p0;
       En = (elem_ok && gl >= 0 && gl < g.NLg) ? Ep[0] : 0.0;
     }
-    __syncthreads();
+    if (NSYNC) {
+      ++it;
+      __syncwarp();
+      if (tx == 0) {
+        __threadfence_block();
+        *(volatile int*)&sflag[ty] = it;
+      }
+      int spins = 0;
+      if (ty >= 1)
+        while (*(volatile int*)&sflag[ty - 1] < it && ++spins < (1 << 26)) {
+        }
+      if (ty + 1 < TY)
+        while (*(volatile int*)&sflag[ty + 1] < it && ++spins < (1 << 26)) {
+        }
+      if (spins >= (1 << 26)) st->nonfinite = 3;  // a neighbouring row never published: report, do not hang
+      __threadfence_block();
+      __syncwarp();
+    } else {
+      __syncthreads();
+    }
     if (ty >= 1) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
