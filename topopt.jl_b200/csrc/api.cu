@@ -340,7 +340,6 @@ int launch_hex8(topopt_handle* h, const double* x, double* y, int fin, const dou
     if (h->kxu_ty == 8) return launch_hex8_modal<8, DOT, FUSEP, PEER, true>(h, x, y, fin, r, pnew);
     if (h->kxu_ty == 16) return launch_hex8_modal<16, DOT, FUSEP, PEER, true>(h, x, y, fin, r, pnew);
     if (h->kxu_ty == 14) return launch_hex8_modal<14, DOT, FUSEP, PEER, true>(h, x, y, fin, r, pnew);
-    if (h->kxu_ty == 20) return launch_hex8_modal<20, DOT, FUSEP, PEER, true>(h, x, y, fin, r, pnew);
     return launch_hex8_modal<12, DOT, FUSEP, PEER, true>(h, x, y, fin, r, pnew);
   }
   if (h->kxu_ty == 8) return launch_hex8_modal<8, DOT, FUSEP, PEER, false>(h, x, y, fin, r, pnew);
@@ -547,7 +546,6 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
     res->tol = h->h_st->tol;
     res->solve_ms = ms;
   }
-  if (h->h_st->nonfinite == 3) return fail(h, TOPOPT_ERR_CUDA, "K.u kernel: intra-CTA neighbour synchronisation timed out");
   if (h->h_st->nonfinite == 2)
     return fail(h, TOPOPT_ERR_NCCL, "peer-memory wait timed out: a neighbouring rank stopped participating");
   if (h->h_st->nonfinite)
