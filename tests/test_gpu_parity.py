@@ -463,3 +463,28 @@ def test_config5_heat_full_size(lib):
     gf = S.pullback(g)
     assert abs(gf.sum() - g.sum()) / abs(g.sum()) < 0.05      # smoothing roughly preserves the mean
     S.close(); s.close()
+
+
+@pytest.mark.parametrize("nels", [(64, 30, 18), (33, 8, 4), (31, 16, 4)])
+def test_hex8_modal_kernel_multi_tile_parity(lib, nels):
+    """The modal K.u kernel tiles the grid in 30 x 14 node-column patches and marches persistent CTAs
+    over (tile, plane) ranges: grids spanning several tiles / ragged last tiles must still match the
+    reference operator to rounding (the oracle's direct solve is only affordable on the small one)."""
+    t = lib
+    prob, oprob = t.PointLoadCantilever(nels), o.PointLoadCantilever(nels)
+    prob.Ke = oprob.Ke.copy()
+    s = make_solver(t, prob, abstol=1e-11, reltol=0.0, cg_max_iter=50000)
+    rho = rand_rho(prob.nel, 11)
+    E = o.get_rho(rho, 3.0, 1e-3)
+    s.set_density(rho)
+    for zero_fixed in (True, False):
+        x = rand_x(oprob, seed=4, zero_fixed=zero_fixed)
+        assert rel(s.mul(x), o.matfree_mul(oprob, E, x)) < RTOL_OP
+    if oprob.nel < 2000:
+        comp = t.ComplianceFun(s)
+        val, grad = comp.value_and_grad(rho)
+        u = o.solve_direct(oprob, E)
+        obj, _, g = o.compliance(oprob, u, rho, 3.0, 1e-3)
+        assert s.last_result.converged == 1
+        assert abs(val - obj) / obj < RTOL_SOLVE and rel(grad, g) < RTOL_SOLVE
+    s.close()

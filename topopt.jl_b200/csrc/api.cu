@@ -77,7 +77,7 @@ struct topopt_handle {
   double Ke[kMaxKe * kMaxKe];
   double Kh[48];          // modal coefficients (hex8 elasticity fast path)
   bool modal_ok = false;  // Ke has the brick/isotropic modal sparsity pattern
-  int kxu_ty = 16, kxu_zc = 16, kxu_waves = 1, kxu_nsync = 1;
+  int kxu_ty = 16, kxu_waves = 1, kxu_nsync = 1;
   double fixed_diag = 0.0, cellvol = 1.0;
   double sizes[3] = {1, 1, 1};
   // device buffers
@@ -310,7 +310,6 @@ int launch_hex8_modal(topopt_handle* h, const double* x, double* y, int fin, con
   const Geo& g = h->g;
   const int tilesX = (g.NX + 29) / 30, tilesY = (g.NY + TY - 3) / (TY - 2);
   // persistent grid: resident CTAs per SM (register-limited) x 148 SMs, capped by the work
-  const int zc = h->kxu_zc;
   const int per_sm = TY <= 4 ? 4 : (TY <= 8 ? 2 : 1);
   int grid = 148 * per_sm * std::max(1, h->kxu_waves);
   const long long units = (long long)tilesX * tilesY * g.nown;
@@ -329,7 +328,7 @@ int launch_hex8_modal(topopt_handle* h, const double* x, double* y, int fin, con
     if (h->peer_p_hi) xhi = h->peer_p_hi + (size_t)h->plane_dofs;
   }
   k_apply_hex8_modal<TY, DOT, FUSEP, PEER, NSYNC><<<grid, 32 * TY, smem, h->stream>>>(g, x, y, h->d_E, h->d_fixed, h->fixed_diag, tilesX,
-                                                                              tilesY, zc, h->d_partials, h->d_st, fin, r, pnew, xlo, xhi);
+                                                                              tilesY, h->d_partials, h->d_st, fin, r, pnew, xlo, xhi);
   h->stats.kernel_launches += 1;
   return check_launch(h, "k_apply_hex8_modal");
 }
@@ -837,7 +836,6 @@ int topopt_create(const topopt_desc* d, topopt_handle** out) {
     if (const char* e = getenv("TOPOPT_KXU_TY")) h->kxu_ty = atoi(e);
     if (getenv("TOPOPT_FUSE_P")) h->no_fuse = false;
     if (getenv("TOPOPT_NO_GRAPH")) h->use_graphs = false;
-    if (const char* e = getenv("TOPOPT_KXU_ZC")) h->kxu_zc = atoi(e);
     if (const char* e = getenv("TOPOPT_KXU_WAVES")) h->kxu_waves = atoi(e);
     if (const char* e = getenv("TOPOPT_KXU_NSYNC")) h->kxu_nsync = atoi(e);
   }

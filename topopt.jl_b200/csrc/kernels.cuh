@@ -215,18 +215,6 @@ __device__ __forceinline__ void block_partials_finish(const double (&v)[NS], dou
   }
 }
 
-// after the direction update: tell both slab neighbours that this rank's boundary planes of p are
-// final for handshake number halo_seq (they read them directly over NVLink inside K.u)
-__global__ void k_signal_halo(CGState* st) {
-  PeerComm* pc = st->peer;
-  if (st->done) return;
-  const unsigned long long seq = pc->halo_seq + 1;
-  __threadfence_system();
-  if (pc->rank + 1 < pc->world) *(volatile unsigned long long*)&pc->block[pc->rank + 1]->halo_flag[0] = seq;
-  if (pc->rank > 0) *(volatile unsigned long long*)&pc->block[pc->rank - 1]->halo_flag[1] = seq;
-  pc->halo_seq = seq;
-}
-
 __global__ void k_finalize(CGState* st, int which) {
   if (which == FIN_INIT || !st->done) cg_finalize(st, which);
 }
@@ -575,12 +563,6 @@ __global__ void __launch_bounds__(kBlock) k_dot(long long off, long long n, cons
        t += (long long)gridDim.x * blockDim.x)
     v[0] = fma(a[off + t], b[off + t], v[0]);
   block_partials_finish<1>(v, partials, st, FIN_PLAIN, sm);
-}
-
-__global__ void k_zero_entries(long long n, const int* __restrict__ idx, double* __restrict__ v) {
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
-       t += (long long)gridDim.x * blockDim.x)
-    v[idx[t]] = 0.0;
 }
 
 // zero prescribed dofs of a local vector using the node flags (apply_zero!)

@@ -7,13 +7,15 @@
 // costs ~200 fp64 instructions instead of 576 DFMA.  The pattern is verified numerically on the
 // host for the Ke the caller passes; any other Ke falls back to the dense gather kernel.
 //
-// Work decomposition: a CTA of 32 x TY threads loads a 32 x TY patch of node columns, evaluates
-// the 31 x (TY-1) element columns inside it and owns the 30 x (TY-2) interior node columns (every
-// owned node needs its four surrounding element columns); it marches along the slab axis.  Thread (tx,ty) owns node column (i0-1+tx, j0-1+ty) and the element column whose lower
-// corner is that node.  Per step it loads ONE new node (3 doubles), gets the x+1 neighbour by
-// warp shuffle and the y+1 row through shared memory, evaluates its element in registers, and
-// the eight corner forces are reduced back onto nodes with a shuffle (x) and one shared-memory
-// hop (y); the z direction is a register carry.  No atomics, fixed summation order.
+// Work decomposition: a persistent CTA of 32 x TY threads (one per SM) loads a 32 x TY patch of node
+// columns, evaluates the 31 x (TY-1) element columns inside it and owns the 30 x (TY-2) interior node
+// columns; it marches along the slab axis over an equal share of the linearised (tile, plane) space.
+// Thread (tx,ty) owns node column (i0-1+tx, j0-1+ty) and the element column whose lower corner is that
+// node.  Per step it loads ONE new node (3 doubles, prefetched two planes ahead), forms the z stage of
+// the Hadamard transform once per node column and shares it (x+1 by warp shuffle, y+1 row through
+// shared memory), evaluates its element in registers, and the corner forces are reduced onto node
+// columns before the inverse z stage (x by shuffle, y by one shared-memory hop); z is a register
+// carry.  Rows synchronise only with their two neighbours.  No atomics, fixed summation order.
 #pragma once
 #include "kernels.cuh"
 
@@ -50,7 +52,7 @@ inline const ModalEntry* modal_pattern() {
 template <int TY, bool DOT, bool FUSEP, bool PEER, bool NSYNC>
 __global__ void __launch_bounds__(32 * TY, (TY <= 4 ? 4 : (TY <= 8 ? 2 : 1)))
     k_apply_hex8_modal(Geo g, const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ E,
-                       const unsigned char* __restrict__ fixed, double fixed_diag, int tilesX, int tilesY, int zc,
+                       const unsigned char* __restrict__ fixed, double fixed_diag, int tilesX, int tilesY,
                        double* partials, CGState* st, int fin, const double* __restrict__ rvec, double* __restrict__ pnew,
                        const double* __restrict__ xlo, const double* __restrict__ xhi) {
   extern __shared__ double smem_dyn[];
@@ -75,11 +77,10 @@ __global__ void __launch_bounds__(32 * TY, (TY <= 4 ? 4 : (TY <= 8 ? 2 : 1)))
   double dot = 0.0;
   // Persistent CTAs: the (tile, plane) space is linearised and cut into gridDim.x equal ranges,
   // so every CTA marches the same number of planes (no wave quantisation, and only one redundant
-  // priming layer per segment).  `zc` is unused in this scheme.
+  // priming layer per segment).
   const long long units = (long long)tilesX * tilesY * g.nown;
   long long u0 = units * blockIdx.x / gridDim.x;
   const long long u1 = units * (blockIdx.x + 1) / gridDim.x;
-  (void)zc;
   while (u0 < u1) {
   const int tile = (int)(u0 / g.nown);
   const int zoff = (int)(u0 % g.nown);
@@ -194,13 +195,8 @@ __global__ void __launch_bounds__(32 * TY, (TY <= 4 ? 4 : (TY <= 8 ? 2 : 1)))
       D[1][c] = __shfl_down_sync(FULL, D0[c], 1);
       S[2][c] = sX[par][c][ty + 1 < TY ? ty + 1 : ty][tx];
       D[2][c] = sX[par][3 + c][ty + 1 < TY ? ty + 1 : ty][tx];
-#ifdef TOPOPT_KXU_LDS_CORNER
-      S[3][c] = sX[par][c][ty + 1 < TY ? ty + 1 : ty][tx < 31 ? tx + 1 : tx];
-      D[3][c] = sX[par][3 + c][ty + 1 < TY ? ty + 1 : ty][tx < 31 ? tx + 1 : tx];
-#else
       S[3][c] = __shfl_down_sync(FULL, S[2][c], 1);
       D[3][c] = __shfl_down_sync(FULL, D[2][c], 1);
-#endif
     }
     // x, y stages -> modal coefficients scaled by E_e (the constant mode is never needed)
     double X[3], Y[3], Z[3], XY[3], YZ[3], XZ[3], XYZ[3];
