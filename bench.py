@@ -98,40 +98,55 @@ def workload_name(nels):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_port_sample(nels, cg_iters, openmp, maxiter):
-    """Times the C port on a bounded sample: cg_iters CG iterations + 1 compliance/sensitivity +
-    2 filter passes, extrapolated to a `maxiter`-iteration SIMP evaluation."""
-    import ref_c
-    import topopt_jl_b200 as t
+class CpuPort:
+    """The C port of the reference's CPU path (oracle/topopt_ref.c) set up once for a grid."""
 
-    prob = t.PointLoadCantilever(nels)
-    R = ref_c.RefProblem(3, 3, nels, prob.Ke, prob.prescribed_dofs, openmp=openmp, native=True)
-    rho = np.full(prob.nel, VOLFRAC)
-    t0 = time.perf_counter()
-    xf = R.filter(RMIN, rho)
-    t_filter = time.perf_counter() - t0
-    R.set_density(xf, PENAL, XMIN)
-    b = prob.fixedload.copy()
-    b[prob.prescribed_dofs - 1] = 0.0
-    t0 = time.perf_counter()
-    u, it, _ = R.cg(b, abstol=0.0, reltol=0.0, maxiter=cg_iters)
-    t_cg = (time.perf_counter() - t0) / max(it, 1)
-    t0 = time.perf_counter()
-    R.compliance(u, xf, PENAL, XMIN)
-    t_sens = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    y = np.empty(prob.ndof)
-    for _ in range(2):
-        y = R.mul(u)
-    t_mul = (time.perf_counter() - t0) / 2
-    threads = R.threads
-    R.close()
-    step = maxiter * t_cg + t_sens + 2 * t_filter
-    return {
-        "step_s": step, "t_cg_iter_s": t_cg, "t_mul_s": t_mul, "t_sens_s": t_sens, "t_filter_s": t_filter, "threads": threads,
-        "sample": f"{cg_iters} of {maxiter} CG iterations + 1 compliance/sensitivity + 1 filter pass at {'x'.join(map(str, nels))}, SIMP step extrapolated as {maxiter}*t_cg + t_sens + 2*t_filter",
-        "kxu_gdofs": prob.ndof / t_mul / 1e9,
-    }
+    def __init__(self, nels, openmp):
+        import ref_c
+        import topopt_jl_b200 as t
+
+        self.nels = nels
+        self.prob = t.PointLoadCantilever(nels)
+        self.R = ref_c.RefProblem(3, 3, nels, self.prob.Ke, self.prob.prescribed_dofs, openmp=openmp, native=True)
+        self.b = self.prob.fixedload.copy()
+        self.b[self.prob.prescribed_dofs - 1] = 0.0
+
+    def sample(self, cg_iters, maxiter):
+        """Times a bounded sample: 1 filter pass, cg_iters CG iterations, 1 compliance/sensitivity,
+        2 K.u applications; the SIMP step is extrapolated to `maxiter` CG iterations."""
+        R, prob = self.R, self.prob
+        rho = np.full(prob.nel, VOLFRAC)
+        t0 = time.perf_counter()
+        xf = R.filter(RMIN, rho)
+        t_filter = time.perf_counter() - t0
+        R.set_density(xf, PENAL, XMIN)
+        t0 = time.perf_counter()
+        u, it, _ = R.cg(self.b, abstol=0.0, reltol=0.0, maxiter=cg_iters)
+        t_cg = (time.perf_counter() - t0) / max(it, 1)
+        t0 = time.perf_counter()
+        R.compliance(u, xf, PENAL, XMIN)
+        t_sens = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for _ in range(2):
+            R.mul(u)
+        t_mul = (time.perf_counter() - t0) / 2
+        step = maxiter * t_cg + t_sens + 2 * t_filter
+        return {
+            "step_s": step, "t_cg_iter_s": t_cg, "t_mul_s": t_mul, "t_sens_s": t_sens, "t_filter_s": t_filter, "threads": R.threads,
+            "sample": f"{cg_iters} of {maxiter} CG iterations + 1 compliance/sensitivity + 1 filter pass at {'x'.join(map(str, self.nels))}, SIMP step extrapolated as {maxiter}*t_cg + t_sens + 2*t_filter",
+            "kxu_gdofs": prob.ndof / t_mul / 1e9,
+        }
+
+    def close(self):
+        self.R.close()
+
+
+def cpu_port_sample(nels, cg_iters, openmp, maxiter):
+    port = CpuPort(nels, openmp)
+    try:
+        return port.sample(cg_iters, maxiter)
+    finally:
+        port.close()
 
 
 def run_reference(args, nels):
@@ -140,11 +155,13 @@ def run_reference(args, nels):
         return
     vals = []
     info = None
-    for _ in range(args.warmup if args.warmup < 1 else 1):
-        cpu_port_sample(nels, 1, True, args.maxiter)
+    port = CpuPort(nels, openmp=True)
+    for _ in range(min(args.warmup, 1)):
+        port.sample(1, args.maxiter)
     for _ in range(args.steps):
-        info = cpu_port_sample(nels, args.ref_cg_iters, True, args.maxiter)
+        info = port.sample(args.ref_cg_iters, args.maxiter)
         vals.append(info["step_s"])
+    port.close()
     step = float(np.mean(vals))
     v = 1.0 / step
     line = {
