@@ -1,0 +1,25 @@
+"""bench.py contract on CPU: the reference arm (`--impl reference`) prints exactly one JSON line on
+stdout with the keys the driver reads (tiny grid so it runs in seconds without a GPU)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_json_line():
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--nels", "12,4,4", "--steps", "2", "--warmup", "1",
+           "--ref-cg-iters", "3"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["metric"] == "simp_iterations_per_sec" and d["dtype"] == "f64"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["vs_baseline"] is None and "workload" in d["config"]
