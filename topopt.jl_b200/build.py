@@ -12,6 +12,7 @@ SOURCES = [os.path.join(HERE, "csrc", "api.cu"), os.path.join(HERE, "csrc", "hos
 DEPS = SOURCES + [
     os.path.join(HERE, "csrc", "kernels.cuh"),
     os.path.join(HERE, "csrc", "kxu_hex8.cuh"),
+    os.path.join(HERE, "csrc", "kxu_hex8_2row.cuh"),
     os.path.join(HERE, "csrc", "common.h"),
     os.path.join(ROOT, "include", "topopt_cuda.h"),
 ]

@@ -18,6 +18,7 @@
 #include "common.h"
 #include "kernels.cuh"
 #include "kxu_hex8.cuh"
+#include "kxu_hex8_2row.cuh"
 
 using namespace topopt;
 
@@ -77,7 +78,7 @@ struct topopt_handle {
   double Ke[kMaxKe * kMaxKe];
   double Kh[48];          // modal coefficients (hex8 elasticity fast path)
   bool modal_ok = false;  // Ke has the brick/isotropic modal sparsity pattern
-  int kxu_ty = 16, kxu_waves = 1, kxu_nsync = 1;
+  int kxu_ty = 16, kxu_waves = 1, kxu_nsync = 1, kxu_2row = 1;  // 2row: 0 = one-row kernel, 1 = auto, else thread rows
   double fixed_diag = 0.0, cellvol = 1.0;
   double sizes[3] = {1, 1, 1};
   // device buffers
@@ -333,8 +334,55 @@ int launch_hex8_modal(topopt_handle* h, const double* x, double* y, int fin, con
   return check_launch(h, "k_apply_hex8_modal");
 }
 
+template <int TYT, bool DOT, bool PEER>
+int launch_hex8_modal2(topopt_handle* h, const double* x, double* y, int fin) {
+  const Geo& g = h->g;
+  constexpr int ROWS = 2 * TYT - 2;
+  const int tilesX = (g.NX + 29) / 30, tilesY = (g.NY + ROWS - 1) / ROWS;
+  int grid = 148 * std::max(1, h->kxu_waves);
+  const long long units = (long long)tilesX * tilesY * g.nown;
+  if (grid > units) grid = (int)units;
+  const size_t smem = sizeof(double) * 2 * 12 * TYT * 32;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(h, cudaFuncSetAttribute(k_apply_hex8_modal2<TYT, DOT, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const double* xlo = nullptr;
+  const double* xhi = nullptr;
+  if (PEER) {
+    if (h->peer_p_lo) xlo = h->peer_p_lo + (size_t)h->plane_dofs * h->nown_lower;
+    if (h->peer_p_hi) xhi = h->peer_p_hi + (size_t)h->plane_dofs;
+  }
+  k_apply_hex8_modal2<TYT, DOT, PEER><<<grid, 32 * TYT, smem, h->stream>>>(g, x, y, h->d_E, h->d_fixed, h->fixed_diag, tilesX, tilesY,
+                                                                          h->d_partials, h->d_st, fin, xlo, xhi);
+  h->stats.kernel_launches += 1;
+  return check_launch(h, "k_apply_hex8_modal2");
+}
+
 template <bool DOT, bool FUSEP, bool PEER = false>
 int launch_hex8(topopt_handle* h, const double* x, double* y, int fin, const double* r, double* pnew) {
+  if (h->kxu_2row && !FUSEP) {
+    int tyt = h->kxu_2row;
+    if (tyt == 1) {  // auto: thread rows per CTA that waste the fewest node rows for this grid
+      double best = -1.0;
+      const int cand[3] = {12, 10, 8};
+      const double speed[3] = {1.0, 0.97, 0.93};  // measured relative efficiency of the variants
+      for (int k = 0; k < 3; ++k) {
+        const int rows = 2 * cand[k] - 2;
+        const int tiles = (h->g.NY + rows - 1) / rows;
+        const double eff = speed[k] * (double)h->g.NY / ((double)tiles * (rows + 2));
+        if (eff > best) {
+          best = eff;
+          tyt = cand[k];
+        }
+      }
+    }
+    if (tyt == 10) return launch_hex8_modal2<10, DOT, PEER>(h, x, y, fin);
+    if (tyt == 14) return launch_hex8_modal2<14, DOT, PEER>(h, x, y, fin);
+    if (tyt == 8) return launch_hex8_modal2<8, DOT, PEER>(h, x, y, fin);
+    return launch_hex8_modal2<12, DOT, PEER>(h, x, y, fin);
+  }
   if (h->kxu_nsync) {
     if (h->kxu_ty == 8) return launch_hex8_modal<8, DOT, FUSEP, PEER, true>(h, x, y, fin, r, pnew);
     if (h->kxu_ty == 16) return launch_hex8_modal<16, DOT, FUSEP, PEER, true>(h, x, y, fin, r, pnew);
@@ -838,6 +886,7 @@ int topopt_create(const topopt_desc* d, topopt_handle** out) {
     if (getenv("TOPOPT_NO_GRAPH")) h->use_graphs = false;
     if (const char* e = getenv("TOPOPT_KXU_WAVES")) h->kxu_waves = atoi(e);
     if (const char* e = getenv("TOPOPT_KXU_NSYNC")) h->kxu_nsync = atoi(e);
+    if (const char* e = getenv("TOPOPT_KXU_2ROW")) h->kxu_2row = atoi(e);
   }
 
   // slab partition along the last axis
