@@ -268,6 +268,16 @@ __global__ void __launch_bounds__(32 * TYT, 1)
           En[r] = load_E(r, ll + 2);
         }
       }
+      // raw x of the plane being stored (p.Ap and prescribed rows): issued here so that the L1
+      // latency overlaps the neighbour wait; few registers are live at this point
+      double xd[2][3];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const bool need = own[r] && ll >= z0 && (DOT || fcur[r]);
+        const double* xp = x + ((long long)ll * g.S + ncol[r]) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) xd[r][c] = need ? xp[c] : 0.0;
+      }
       // ---- neighbour-only synchronisation (see kxu_hex8.cuh)
       ++it;
       __syncwarp();
@@ -299,9 +309,9 @@ __global__ void __launch_bounds__(32 * TYT, 1)
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             double v = carry[r][c] + (n[0][c] - n[1][c]);
-            if (fcur[r] & (1 << c)) v = fixed_diag * x[yo + c];  // prescribed row: meandiag * x (raw value, rare path)
+            if (fcur[r] & (1 << c)) v = fixed_diag * xd[r][c];  // prescribed row: meandiag * x (raw value)
             y[yo + c] = v;
-            if (DOT) dot = fma(x[yo + c], v, dot);
+            if (DOT) dot = fma(xd[r][c], v, dot);
           }
         }
 #pragma unroll
