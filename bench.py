@@ -46,42 +46,53 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region: one streaming
+    `nvidia-smi -lms 100` process started just before the region and stopped right after it."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
         self.index = index
-        self.samples = []
-        self._stop = threading.Event()
+        self.lines = []
+        self._p = None
         self._t = None
 
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(
-                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                    capture_output=True, text=True, timeout=5,
-                ).stdout.strip()
-                if out:
-                    self.samples.append([c.strip() for c in out.splitlines()[0].split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+    def _pump(self):
+        try:
+            for ln in self._p.stdout:
+                self.lines.append(ln)
+        except Exception:
+            pass
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        try:
+            self._p = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            self._t = threading.Thread(target=self._pump, daemon=True)
+            self._t.start()
+            time.sleep(0.25)  # first sample lands before the timed region starts
+        except Exception:
+            self._p = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self._p is not None:
+            time.sleep(0.12)
+            self._p.terminate()
+            try:
+                self._p.wait(timeout=5)
+            except Exception:
+                self._p.kill()
+            if self._t is not None:
+                self._t.join(timeout=2)
 
     def summary(self):
         sm, mx, reasons = [], 0.0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for ln in self.lines:
+            s = [c.strip() for c in ln.split(",")]
             try:
                 sm.append(float(s[0]))
                 mx = max(mx, float(s[1]))
@@ -91,6 +102,17 @@ class ClockSampler:
             except Exception:
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ncu_traffic(world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per K.u launch from the committed ncu capture
+    (profiles/ncu_traffic.json); only recorded for the single-GPU configuration-4 kernel."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            d = json.load(f)
+        return d.get(f"n{world}", {}).get("kxu_dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 def workload_name(nels):
@@ -259,6 +281,9 @@ def run_native(args, nels):
         dist.all_reduce(tk, op=dist.ReduceOp.MAX)
     kxu_ms, cg_ms = float(tk[0].item()), float(tk[1].item())
     peak, peak_src = measured_peaks()
+    nown = nels[2] // world + (1 if world == 1 else 0)
+    kxu_name = ("k_apply_hex8_modal2<12> (matrix-free hex8 K.u, two node rows per thread)" if nown >= 96
+                else "k_apply_hex8_modal<16> (matrix-free hex8 K.u)")
     kxu_bytes_total = 16 * prob.ndof + 8 * prob.nel  # read x, write y, read E_e
     kxu_bytes_launch = kxu_bytes_total / world       # one launch per rank over its slab
     achieved = kxu_bytes_launch / (kxu_ms * 1e-3) / 1e9
@@ -281,8 +306,9 @@ def run_native(args, nels):
             "e2e": {"value": args.steps / wall_e2e, "unit": "it/s", "h2d_bytes_per_step": int(st2.h2d_bytes // args.steps),
                     "d2h_bytes_per_step": int(st2.d2h_bytes // args.steps) + 8, "objective": obj_e2e},
             "gpu_launches": launches,
-            "roofline": {"kernel": "k_apply_hex8_modal<12> (matrix-free hex8 K.u)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "roofline": {"kernel": kxu_name, "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(world) if nels == DEFAULT_NELS else None,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": kxu_bytes_launch, "ms_per_launch": kxu_ms},
             "kxu_gdofs": prob.ndof / (kxu_ms * 1e-3) / 1e9,
             "cg_iteration": {"ms": cg_ms, "it_per_s": 1e3 / cg_ms, "achieved_gbs": cg_bytes / (cg_ms * 1e-3) / 1e9,

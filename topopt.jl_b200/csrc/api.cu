@@ -362,7 +362,9 @@ int launch_hex8_modal2(topopt_handle* h, const double* x, double* y, int fin) {
 
 template <bool DOT, bool FUSEP, bool PEER = false>
 int launch_hex8(topopt_handle* h, const double* x, double* y, int fin, const double* r, double* pnew) {
-  if (h->kxu_2row && !FUSEP) {
+  // Two node rows per thread win on thick slabs (single GPU: +6 %); on thin slabs (>= 4 ranks at
+  // config 4) the persistent CTAs' segments get short and the one-row kernel measured 8-15 % faster.
+  if (h->kxu_2row && !FUSEP && (h->kxu_2row != 1 || h->g.nown >= 96)) {
     int tyt = h->kxu_2row;
     if (tyt == 1) {  // auto: thread rows per CTA that waste the fewest node rows for this grid
       double best = -1.0;
