@@ -53,6 +53,22 @@ def test_csc_pattern_bit_exact(lib, nels, ncomp):
     assert np.array_equal(colptr - 1, cp) and np.array_equal(rowval - 1, rv)
 
 
+def test_library_matches_reference_goldens_directly(lib):
+    """The library's host entry points against the reference's golden integers themselves
+    (tests/golden/reference_goldens.json), not only through the oracle."""
+    import json
+
+    t = lib
+    G = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_goldens.json")))
+    md = t.Metadata(2, 2, (2, 2))
+    assert md.cells.tolist() == G["halfmbb_2x2"]["cells"]
+    assert md.node_dofs.tolist() == G["halfmbb_2x2"]["node_dofs"]
+    assert md.cell_dofs.tolist() == G["halfmbb_2x2"]["cell_dofs"]
+    assert t.PointLoadCantilever((160, 40)).force_dof == G["force_dofs"]["PointLoadCantilever_160x40"]
+    assert t.HalfMBB((60, 20)).force_dof == G["force_dofs"]["HalfMBB_60x20"]
+    assert len(t.HeatTree(tuple(G["heat_tree"]["nels"])).prescribed_dofs) == G["heat_tree"]["n_prescribed"]
+
+
 def test_config_sizes(lib):
     """SURVEY 8 config table (ndof, nnz) from the closed forms in the library."""
     t = lib

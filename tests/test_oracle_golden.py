@@ -3,36 +3,38 @@ hold for this path, and re-runs the reference tests' floating-point *properties*
 Golden integers: test/topopt_problems/metadata.jl:53-132, problems.jl:20,63.
 There are no golden floating-point vectors in the reference: "parity unpinned" for
 floats, which are therefore covered by properties only."""
+import json
+import os
+
 import numpy as np
 import pytest
 
 import topopt_oracle as o
 
 
+GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_goldens.json")))
+
+
 def test_golden_metadata_halfmbb_2x2():
     """test/topopt_problems/metadata.jl:53-132 (HalfMBB((2,2),(1.,1.),1.,0.3,1.))"""
+    G = GOLD["halfmbb_2x2"]
     p = o.HalfMBB((2, 2))
-    coords = [(0.0, 0.0), (1.0, 0.0), (2.0, 0.0), (0.0, 1.0), (1.0, 1.0), (2.0, 1.0), (0.0, 2.0), (1.0, 2.0), (2.0, 2.0)]
-    assert [tuple(x) for x in p.grid.nodes] == coords
-    assert (p.grid.cells + 1).tolist() == [[1, 2, 5, 4], [2, 3, 6, 5], [4, 5, 8, 7], [5, 6, 9, 8]]
-    node_dofs = [[1, 3, 9, 7, 5, 11, 15, 13, 17], [2, 4, 10, 8, 6, 12, 16, 14, 18]]
-    assert (p.metadata.node_dofs + 1).tolist() == node_dofs
-    cell_dofs = [[1, 3, 7, 5], [2, 4, 8, 6], [3, 9, 5, 11], [4, 10, 6, 12], [5, 11, 13, 17], [6, 12, 14, 18], [7, 5, 15, 13], [8, 6, 16, 14]]
-    assert (p.metadata.cell_dofs + 1).tolist() == cell_dofs
+    assert [list(x) for x in p.grid.nodes] == G["coords"]
+    assert (p.grid.cells + 1).tolist() == G["cells"]
+    assert (p.metadata.node_dofs + 1).tolist() == G["node_dofs"]
+    assert (p.metadata.cell_dofs + 1).tolist() == G["cell_dofs"]
     md = p.metadata
     for d in range(1, md.ndof + 1):  # dof_cells is the inverse of cell_dofs (metadata.jl:97-104)
         for c, l in md.dof_cells_1based(d):
             assert md.cell_dofs[l - 1, c - 1] + 1 == d
-    expected = {1: [(1, 1)], 2: [(1, 2), (2, 1)], 3: [(2, 2)], 4: [(1, 4), (3, 1)], 5: [(1, 3), (2, 4), (3, 2), (4, 1)],
-                6: [(2, 3), (4, 2)], 7: [(3, 4)], 8: [(3, 3), (4, 4)], 9: [(4, 3)]}
-    for n, lst in expected.items():
-        assert md.node_cells_1based(n) == lst
+    for n, lst in G["node_cells"].items():
+        assert md.node_cells_1based(int(n)) == [tuple(x) for x in lst]
 
 
 def test_golden_force_dofs():
     """test/topopt_problems/problems.jl:20 and :63"""
-    assert o.PointLoadCantilever((160, 40)).force_dof + 1 == 161 * 21 * 2
-    assert o.HalfMBB((60, 20)).force_dof + 1 == (61 * 20 + 2) * 2
+    assert o.PointLoadCantilever((160, 40)).force_dof + 1 == GOLD["force_dofs"]["PointLoadCantilever_160x40"] == 161 * 21 * 2
+    assert o.HalfMBB((60, 20)).force_dof + 1 == GOLD["force_dofs"]["HalfMBB_60x20"] == (61 * 20 + 2) * 2
 
 
 def test_numbering_loop_equals_vectorised():
