@@ -169,3 +169,32 @@ def test_c_port_matches_numpy_oracle(openmp):
         assert abs(obj - oo) < 1e-12 * abs(oo) and np.max(np.abs(g - go)) < 1e-12 * np.max(np.abs(go))
         assert np.max(np.abs(R.filter(2.0, rho) - o.SensFilter(p, 2.0).pullback(rho))) < 1e-14
         R.close()
+
+
+def test_modal_pattern_table_covers_brick_element_matrices():
+    """The fast hex8 kernel hard-codes which entries of Khat = T' Ke T / 64 can be non-zero
+    (modal_pattern() in csrc/kxu_hex8.cuh).  Parse that table and check it against the oracle's Ke
+    for cubes, bricks and several Poisson ratios: every non-zero of Khat must be in the table."""
+    src = open(os.path.join(ROOT, "topopt.jl_b200", "csrc", "kxu_hex8.cuh")).read()
+    body = src[src.index("static const ModalEntry p[45]"):src.index("return p;")]
+    pat = [(int(a), int(b)) for a, b in re.findall(r"\{(\d+),\s*(\d+)\}", body)]
+    assert len(pat) == 45 and len(set(pat)) == 45
+    corners = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]
+    modes = [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (0, 1, 1), (1, 0, 1), (1, 1, 1)]
+    H = np.array([[np.prod([(2 * c[d] - 1) ** m[d] for d in range(3)]) for m in modes] for c in corners], dtype=float)
+    T = np.kron(H, np.eye(3))
+    allowed = np.zeros((24, 24), dtype=bool)
+    for r, c in pat:
+        allowed[r, c] = True
+    assert np.array_equal(allowed, allowed.T)
+    for sizes in ((1.0, 1.0, 1.0), (1.0, 0.5, 2.0), (0.3, 0.3, 1.7)):
+        for nu in (0.0, 0.3, 0.45):
+            Ke = o.element_stiffness(3, sizes, 2.5, nu)
+            Kh = T.T @ Ke @ T / 64.0
+            assert np.max(np.abs(Kh[~allowed])) < 1e-12 * np.max(np.abs(Kh))
+            assert np.max(np.abs(T @ Kh @ T.T - Ke)) < 1e-12 * np.max(np.abs(Ke))  # Ke = T Khat T'
+    # an anisotropic / distorted matrix must NOT pass the check (the library then uses the dense kernel)
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((24, 24))
+    Kh = T.T @ (A @ A.T) @ T / 64.0
+    assert np.max(np.abs(Kh[~allowed])) > 1e-3 * np.max(np.abs(Kh))
