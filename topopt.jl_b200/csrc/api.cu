@@ -399,7 +399,7 @@ int launch_hex8(topopt_handle* h, const double* x, double* y, int fin, const dou
 template <bool DOT>
 int launch_apply(topopt_handle* h, const double* x, double* y, int fin) {
   if (h->dim == 3 && h->nc == 3 && h->modal_ok) return launch_hex8<DOT, false>(h, x, y, fin, nullptr, nullptr);
-  const int grid = DOT ? kReduceBlocks : grid_for((long long)h->g.S * h->g.nown, kWideGrid);
+  const int grid = grid_for((long long)h->g.S * h->g.nown, DOT ? kReduceBlocks : kWideGrid);
 #define CALL(D, C) \
   LAUNCH(h, (k_apply<D, C, DOT>), grid, h->g, x, y, h->d_E, h->d_fixed, h->fixed_diag, h->d_partials, h->d_st, fin)
   DISPATCH(h, CALL);
@@ -411,7 +411,7 @@ template <bool DOT>
 int launch_spmv(topopt_handle* h, const double* x, double* y, int fin) {
   const long long nrows = h->ndof;
   const int lanes = (h->dim == 3 && h->nc == 3) ? 32 : 8;
-  const int grid = DOT ? kReduceBlocks : grid_for(nrows * lanes, kWideGrid);
+  const int grid = grid_for(nrows * lanes, DOT ? kReduceBlocks : kWideGrid);
   if (lanes == 32)
     LAUNCH(h, (k_spmv<32, DOT>), grid, nrows, h->d_rowptr, h->d_col, h->d_nz, x + h->off, y + h->off, h->d_partials,
            h->d_st, fin);
@@ -450,7 +450,8 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
   CUDA_TRY(h, cudaMemcpyAsync(h->d_st, &s, sizeof(CGState), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
   const double* D = pre ? h->d_D : nullptr;
-  const int vgrid = kReduceBlocks;
+  // vector kernels: 4 elements per thread and trip; small problems get a proportionally small grid
+  const int vgrid = (int)std::min<long long>(kReduceBlocks, std::max<long long>(1, (h->nown_dofs + 4 * kBlock - 1) / (4 * kBlock)));
   LAUNCH(h, k_cg_init, vgrid, h->off, h->nown_dofs, b, h->d_u, h->d_r, h->d_p, D, h->d_partials, h->d_st);
   TRY(check_launch(h, "k_cg_init"));
   if (h->world > 1 && !peer) {
