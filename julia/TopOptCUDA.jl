@@ -141,7 +141,7 @@ function (o::ComplianceFun{T,<:GenericFEASolver{T,P,S}})(x::TopOpt.PseudoDensiti
     obj = Ref{Float64}(0.0)
     check(ccall((:topopt_compliance, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}, Ptr{Float64}),
                 handle(s).ptr, C_NULL, obj, o.cell_comp, o.grad), handle(s).ptr)
-    return o.comp = obj[]
+    return obj[]          # cell_comp and grad are filled in place, as compute_compliance does (compliance.jl:89-93)
 end
 
 # (iv) adjoint solves (thermal compliance, DisplacementFun, ...)
