@@ -161,7 +161,7 @@ function LinearAlgebra.mul!(y::AbstractVector, J::CUDAFilterOperator, x::Abstrac
     return y
 end
 Base.:*(J::CUDAFilterOperator{T}, x::AbstractVector) where {T} = mul!(similar(x, T), J, x)
-function CheqFilters.DensityFilterFun(s::GenericFEASolver{T,P,S}, rmin, ::Type{TI}=Int) where {T,P,S<:CUDASolvers,TI}
+function CheqFilters.DensityFilterFun(s::GenericFEASolver{T,P,S}, rmin::Real, ::Type{TI}=Int) where {T,P,S<:CUDASolvers,TI<:Integer}
     out = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:topopt_filter_create, lib), Cint, (Ptr{Cvoid}, Float64, Ref{Ptr{Cvoid}}), handle(s).ptr, rmin, out), handle(s).ptr)
     J = CUDAFilterOperator{T}(out[], length(s.vars), false)
