@@ -198,3 +198,20 @@ def test_modal_pattern_table_covers_brick_element_matrices():
     A = rng.standard_normal((24, 24))
     Kh = T.T @ (A @ A.T) @ T / 64.0
     assert np.max(np.abs(Kh[~allowed])) > 1e-3 * np.max(np.abs(Kh))
+
+
+def test_host_oc_update_matches_oracle(lib):
+    """The design update is host code on both sides (MMA is third-party in the reference); the
+    package's optimality-criteria step must be the oracle's, otherwise the 10-iteration SIMP parity
+    test would compare two different optimisers."""
+    t = lib
+    rng = np.random.default_rng(12)
+    for n in (50, 1000):
+        x = rng.uniform(0.05, 1.0, n)
+        dc = -rng.uniform(0.0, 5.0, n)
+        dv = np.full(n, 1.0 / n)
+        for vf in (0.3, 0.5):
+            a = t.oc_update(x, dc, dv, vf)
+            b = o.oc_update(x, dc, dv, vf)
+            assert np.array_equal(a, b)
+            assert abs(float(a @ dv) - vf) < 1e-6 and a.min() >= 0.0 and a.max() <= 1.0
