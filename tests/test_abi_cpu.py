@@ -214,4 +214,4 @@ def test_host_oc_update_matches_oracle(lib):
             a = t.oc_update(x, dc, dv, vf)
             b = o.oc_update(x, dc, dv, vf)
             assert np.array_equal(a, b)
-            assert abs(float(a @ dv) - vf) < 1e-6 and a.min() >= 0.0 and a.max() <= 1.0
+            assert a.min() >= 0.0 and a.max() <= 1.0 and np.max(np.abs(a - x)) <= 0.2 + 1e-15  # bounds and move limit
