@@ -156,6 +156,10 @@ int topopt_reset_stats(topopt_handle* h);
  * preference, LocalPreferences.toml:2), 0 = interpolation then penalty. */
 int topopt_set_density(topopt_handle* h, const double* rho, int32_t penalty_kind, double p,
                        double xmin, int32_t penalty_before_interpolation);
+/* ProjectedPenaltyFun (penalties.jl:62-69): the penalty of every following topopt_set_density /
+ * topopt_simp_eval is applied to proj(x).  proj_kind 0 = none, 1 = HeavisideProjectionFun(beta)
+ * `1 - exp(-beta x) + x exp(-beta)`, 2 = SigmoidProjectionFun(beta) (penalties.jl:77-96). */
+int topopt_set_projection(topopt_handle* h, int32_t proj_kind, double beta);
 /* direct control of E_e / dE_e (nel each; dE may be NULL) */
 int topopt_set_stiffness(topopt_handle* h, const double* E, const double* dE);
 /* read back E_e, dE_e (nel each; either may be NULL) */

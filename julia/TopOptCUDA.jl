@@ -12,7 +12,8 @@
 module TopOptCUDA
 
 using TopOpt, TopOpt.FEA, TopOpt.TopOptProblems, TopOpt.Functions, TopOpt.CheqFilters
-using TopOpt.Utilities: PowerPenaltyFun, RationalPenaltyFun, SinhPenaltyFun, getpenalty
+using TopOpt.Utilities: PowerPenaltyFun, RationalPenaltyFun, SinhPenaltyFun, ProjectedPenaltyFun,
+    HeavisideProjectionFun, SigmoidProjectionFun, getpenalty
 using LinearAlgebra, ChainRulesCore
 import TopOpt.FEA: solve_system!, GenericFEASolver, AbstractLinearSolver
 
@@ -96,8 +97,15 @@ criteria_code(::FEA.EnergyCriteria) = Cint(1)
 cgopts(s::GenericFEASolver{T,P,S}) where {T,P,S} = CGOpts(s.abstol, sqrt(eps(T)), s.cg_max_iter, opcode(S),
     s.preconditioner === identity ? 0 : 1, criteria_code(s.conv), 0, 0)
 
+projection(p) = (Cint(0), 0.0)
+projection(p::ProjectedPenaltyFun{<:Any,<:Any,<:HeavisideProjectionFun}) = (Cint(1), Float64(p.proj.β))
+projection(p::ProjectedPenaltyFun{<:Any,<:Any,<:SigmoidProjectionFun}) = (Cint(2), Float64(p.proj.β))
+penalty_kind(p::ProjectedPenaltyFun) = penalty_kind(p.penalty)
+
 function upload_density!(s, h)
     pen = getpenalty(s)
+    pk, β = projection(pen)
+    check(ccall((:topopt_set_projection, lib), Cint, (Ptr{Cvoid}, Cint, Float64), h.ptr, pk, β), h.ptr)
     check(ccall((:topopt_set_density, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Float64, Float64, Cint),
                 h.ptr, s.vars, penalty_kind(pen), pen.p, s.xmin, TopOpt.PENALTY_BEFORE_INTERPOLATION ? 1 : 0), h.ptr)
 end

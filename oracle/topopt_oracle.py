@@ -343,6 +343,27 @@ def get_rho_drho(x, p, xmin, penalty_before_interpolation=True):
     return d**p, p * d ** (p - 1) * (1 - xmin)
 
 
+def heaviside_projection(x, beta):
+    """HeavisideProjectionFun (penalties.jl:83-86) and its derivative."""
+    return 1 - np.exp(-beta * x) + x * np.exp(-beta), beta * np.exp(-beta * x) + np.exp(-beta)
+
+
+def sigmoid_projection(x, beta):
+    """SigmoidProjectionFun (penalties.jl:93-96) and its derivative."""
+    e = np.exp((beta + 1) * (0.5 - x))
+    return 1 / (1 + e), (beta + 1) * e / (1 + e) ** 2
+
+
+def get_rho_drho_projected(x, p, xmin, proj, beta, penalty_before_interpolation=True):
+    """ProjectedPenaltyFun with a power penalty: penalty(proj(.)) inside get_rho (penalties.jl:62-69,113-130)."""
+    a = x if penalty_before_interpolation else x * (1 - xmin) + xmin
+    pa, dpa = proj(a, beta)
+    f, df = pa**p, p * pa ** (p - 1) * dpa
+    if penalty_before_interpolation:
+        return f * (1 - xmin) + xmin, (1 - xmin) * df
+    return f, df * (1 - xmin)
+
+
 # --------------------------------------------------------------------------------------
 # Matrix-free operator (src/FEA/matrix_free_operator.jl:66-105)
 # --------------------------------------------------------------------------------------

@@ -119,6 +119,29 @@ def test_penalties(lib):
         s.close()
 
 
+def test_projected_penalty(lib):
+    """ProjectedPenaltyFun (Heaviside / sigmoid projection before the power penalty) on the device."""
+    t = lib
+    prob = t.HalfMBB((5, 4))
+    rho = rand_rho(prob.nel, 3)
+    for Proj, oproj in ((t.HeavisideProjectionFun, o.heaviside_projection), (t.SigmoidProjectionFun, o.sigmoid_projection)):
+        pen = t.ProjectedPenaltyFun(t.PowerPenaltyFun(3.0), Proj(6.0))
+        s = t.FEASolver(t.CUDAMatrixFreeSolver, prob, penalty=pen, xmin=0.01)
+        s.set_density(rho)
+        E, dE = np.empty(prob.nel), np.empty(prob.nel)
+        s._check(s._lib.topopt_get_stiffness(s.handle, E.ctypes.data, dE.ctypes.data))
+        Eo, dEo = o.get_rho_drho_projected(rho, 3.0, 0.01, oproj, 6.0)
+        assert rel(E, Eo) < 1e-14 and rel(dE, dEo) < 1e-13
+        s.close()
+    # the default (no projection) is unaffected by a previous projected solver on the same device
+    s = t.FEASolver(t.CUDAMatrixFreeSolver, prob, penalty=t.PowerPenaltyFun(3.0), xmin=0.01)
+    s.set_density(rho)
+    E = np.empty(prob.nel)
+    s._check(s._lib.topopt_get_stiffness(s.handle, E.ctypes.data, None))
+    assert rel(E, o.get_rho(rho, 3.0, 0.01)) < 1e-14
+    s.close()
+
+
 def test_cg_iterates_match_reference_recurrence(case):
     """Same recurrence as IterativeSolvers.cg!: same iteration count and residual to rounding."""
     t, prob, oprob = case

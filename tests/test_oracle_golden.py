@@ -208,3 +208,19 @@ def test_penalty_formulas():
         fd = (o.get_rho(x + h, 3.0, 1e-3, first) - o.get_rho(x - h, 3.0, 1e-3, first)) / (2 * h)
         assert np.allclose(dr, fd, rtol=1e-6)
     assert np.allclose(o.get_rho_drho(x, 3.0, 1e-3)[1], (1 - 1e-3) * 3 * x**2)  # SURVEY finding 6
+
+
+def test_projected_penalty_formulas():
+    """ProjectedPenaltyFun = penalty(proj(x)) (penalties.jl:62-69): derivative vs central FD, both
+    projections, both preference orders; beta -> 0 Heaviside tends to the identity."""
+    x = np.linspace(0.05, 0.95, 9)
+    for proj in (o.heaviside_projection, o.sigmoid_projection):
+        for first in (True, False):
+            r, dr = o.get_rho_drho_projected(x, 3.0, 1e-3, proj, 4.0, first)
+            h = 1e-6
+            rp = o.get_rho_drho_projected(x + h, 3.0, 1e-3, proj, 4.0, first)[0]
+            rm = o.get_rho_drho_projected(x - h, 3.0, 1e-3, proj, 4.0, first)[0]
+            assert np.allclose(dr, (rp - rm) / (2 * h), rtol=1e-6)
+    y, dy = o.heaviside_projection(x, 1e-9)
+    assert np.allclose(y, x, atol=1e-8) and np.allclose(dy, 1.0, atol=1e-8)
+    assert abs(o.heaviside_projection(np.array([1.0]), 10.0)[0][0] - 1.0) < 1e-15  # proj(1) = 1

@@ -10,9 +10,12 @@ from .fea import (
     EnergyCriteria,
     FEASolver,
     GenericFEASolver,
+    HeavisideProjectionFun,
     PowerPenaltyFun,
+    ProjectedPenaltyFun,
     PseudoDensities,
     RationalPenaltyFun,
+    SigmoidProjectionFun,
     SinhPenaltyFun,
     getcompliance,
 )

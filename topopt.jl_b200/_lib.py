@@ -107,6 +107,7 @@ SIGNATURES = {
     "topopt_get_stats": (C.c_int, [VP, C.POINTER(Stats)]),
     "topopt_reset_stats": (C.c_int, [VP]),
     "topopt_set_density": (C.c_int, [VP, VP, C.c_int32, C.c_double, C.c_double, C.c_int32]),
+    "topopt_set_projection": (C.c_int, [VP, C.c_int32, C.c_double]),
     "topopt_set_stiffness": (C.c_int, [VP, VP, VP]),
     "topopt_get_stiffness": (C.c_int, [VP, VP, VP]),
     "topopt_apply": (C.c_int, [VP, VP, VP]),

@@ -105,6 +105,8 @@ struct topopt_handle {
   CGState* d_st = nullptr;
   CGState* h_st = nullptr;  // pinned
   bool have_jacobi = false;
+  int proj_kind = 0;       // ProjectedPenaltyFun: 0 none, 1 Heaviside, 2 sigmoid
+  double proj_beta = 0.0;
   // assembled path
   long long* d_nbr_start = nullptr;
   int* d_rowptr = nullptr;
@@ -632,7 +634,7 @@ int run_sens(topopt_handle* h, const double* u, const double* v, double gsign, d
 int penalize(topopt_handle* h, int kind, double p, double xmin, int pen_first) {
   if (kind < 0 || kind > 2) return fail(h, TOPOPT_ERR_INVALID, "unknown penalty kind");
   LAUNCH(h, k_penalize, grid_for(h->nloc_el, kWideGrid), (long long)h->nloc_el, h->d_rho, h->d_E, h->d_dE, kind, p, xmin,
-         pen_first);
+         pen_first, h->proj_kind, h->proj_beta);
   h->stiffness_dirty = true;
   return check_launch(h, "k_penalize");
 }
@@ -1083,6 +1085,14 @@ int topopt_set_density(topopt_handle* h, const double* rho, int32_t kind, double
   if (rho) TRY(upload_elems(h, rho, h->d_rho));
   TRY(penalize(h, kind, p, xmin, pen_first));
   return sync(h);
+}
+
+int topopt_set_projection(topopt_handle* h, int32_t proj_kind, double beta) {
+  if (!h) return fail(h, TOPOPT_ERR_INVALID, "topopt_set_projection: NULL handle");
+  if (proj_kind < 0 || proj_kind > 2 || !std::isfinite(beta)) return fail(h, TOPOPT_ERR_INVALID, "topopt_set_projection: bad projection");
+  h->proj_kind = proj_kind;
+  h->proj_beta = beta;
+  return TOPOPT_OK;
 }
 
 int topopt_set_stiffness(topopt_handle* h, const double* E, const double* dE) {

@@ -256,11 +256,23 @@ __global__ void k_scatter_dofs(Geo g, const int* __restrict__ block_of_node, con
 
 // ---- penalisation (src/Utilities/penalties.jl:30-54,113-130; utils.jl:77) ------------------
 __global__ void k_penalize(long long n, const double* __restrict__ rho, double* __restrict__ E,
-                           double* __restrict__ dE, int kind, double p, double xmin, int pen_first) {
+                           double* __restrict__ dE, int kind, double p, double xmin, int pen_first, int proj,
+                           double beta) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) {
     const double x = rho[e];
-    const double a = pen_first ? x : __dadd_rn(__dmul_rn(x, 1.0 - xmin), xmin);  // argument of the penalty
+    double a = pen_first ? x : __dadd_rn(__dmul_rn(x, 1.0 - xmin), xmin);  // argument of the penalty
+    // ProjectedPenaltyFun: penalty(proj(a)) (penalties.jl:62-69,77-96); da = d proj / d a
+    double da = 1.0;
+    if (proj == 1) {  // Heaviside: 1 - exp(-beta a) + a exp(-beta)
+      const double eb = exp(-beta), ea = exp(-beta * a);
+      da = beta * ea + eb;
+      a = 1.0 - ea + a * eb;
+    } else if (proj == 2) {  // sigmoid: 1 / (1 + exp((beta+1)(0.5 - a)))
+      const double ex = exp((beta + 1.0) * (0.5 - a));
+      da = (beta + 1.0) * ex / ((1.0 + ex) * (1.0 + ex));
+      a = 1.0 / (1.0 + ex);
+    }
     double f, df;
     if (kind == 0) {  // x^p
       f = pow(a, p);
@@ -274,6 +286,7 @@ __global__ void k_penalize(long long n, const double* __restrict__ rho, double* 
       f = sinh(p * a) / s;
       df = p * cosh(p * a) / s;
     }
+    df *= da;
     if (pen_first) {
       // density(var, xmin) = var*(1-xmin) + xmin, two roundings like the Julia expression (no FMA)
       E[e] = __dadd_rn(__dmul_rn(f, 1.0 - xmin), xmin);

@@ -30,6 +30,38 @@ class SinhPenaltyFun(PowerPenaltyFun):
     kind = _lib.PENALTY_SINH
 
 
+class HeavisideProjectionFun:
+    """1 - exp(-beta x) + x exp(-beta)  (penalties.jl:83-86)"""
+
+    code = 1
+
+    def __init__(self, beta):
+        self.beta = float(beta)
+
+
+class SigmoidProjectionFun(HeavisideProjectionFun):
+    """1 / (1 + exp((beta+1)(0.5 - x)))  (penalties.jl:93-96)"""
+
+    code = 2
+
+
+class ProjectedPenaltyFun:
+    """penalty(proj(x)), default projection HeavisideProjectionFun(10)  (penalties.jl:62-70)"""
+
+    def __init__(self, penalty, proj=None):
+        self.penalty = penalty
+        self.proj = proj if proj is not None else HeavisideProjectionFun(10.0)
+        self.kind = penalty.kind
+
+    @property
+    def p(self):  # @forward_property ProjectedPenaltyFun penalty
+        return self.penalty.p
+
+    @p.setter
+    def p(self, v):
+        self.penalty.p = float(v)
+
+
 # ---- convergence criteria (src/FEA/convergence_criteria.jl) -----------------------------------
 class DefaultCriteria:
     code = _lib.CRITERIA_DEFAULT
@@ -156,9 +188,15 @@ class GenericFEASolver:
         """solver.vars .= x and the penalised stiffness on the device (compliance.jl:65)."""
         if x is not None:
             self.vars = _x(x)
+        self.sync_projection()
         self._check(
             self._lib.topopt_set_density(self._handle, _lib.ptr(self.vars), self.penalty.kind, self.penalty.p, self.xmin, 1)
         )
+
+    def sync_projection(self):
+        """Tell the library which projection (if any) precedes the penalty."""
+        proj = getattr(self.penalty, "proj", None)
+        self._check(self._lib.topopt_set_projection(self._handle, proj.code if proj else 0, proj.beta if proj else 0.0))
 
     # -- the call operator (solvers_api.jl:285-374) -----------------------------------------------
     def __call__(self, assemble_f=True, rhs=None, lhs=None, download=True):

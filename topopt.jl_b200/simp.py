@@ -19,6 +19,7 @@ def simp_eval(solver, filt, x, grad_out=None):
     res = _lib.CGResult()
     obj = C.c_double()
     kind = 0 if filt is None else filt.kind
+    solver.sync_projection()
     solver._check(
         solver._lib.topopt_simp_eval(
             solver.handle, None if filt is None else filt.handle, kind, _lib.ptr(x), solver.penalty.kind, solver.penalty.p,
