@@ -23,3 +23,19 @@ def test_reference_arm_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["vs_baseline"] is None and "workload" in d["config"]
+
+
+def test_native_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback: on a machine without a CUDA device the native arm must fail loudly instead of
+    silently timing something else."""
+    import torch
+
+    if torch.cuda.is_available():
+        import pytest
+
+        pytest.skip("a GPU is present")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--nels", "8,4,4", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode != 0
+    assert out.stdout.strip() == ""  # no JSON line is fabricated
+    assert "CUDA" in out.stderr or "cuda" in out.stderr
