@@ -217,24 +217,30 @@ def test_host_oc_update_matches_oracle(lib):
             assert a.min() >= 0.0 and a.max() <= 1.0 and np.max(np.abs(a - x)) <= 0.2 + 1e-15  # bounds and move limit
 
 
+C_PROGRAM = r"""
+#include "topopt_cuda.h"
+#include <stdio.h>
+int main(void) {
+  int64_t nels[3] = {4, 2, 2}, nn, ne, nd, nz;
+  int rc = topopt_sizes(3, 3, nels, &nn, &ne, &nd, &nz);
+  printf("%d %lld %lld %lld %lld\n", rc, (long long)nn, (long long)ne, (long long)nd, (long long)nz);
+  return rc;
+}
+"""
+
+
 def test_header_is_plain_c_and_links(tmp_path):
     """include/topopt_cuda.h is the drop-in boundary: it must compile as pedantic C99 (no C++ or
     torch types in the signatures) and the library must link from a C program."""
     import subprocess
 
     src = tmp_path / "abi.c"
-    src.write_text(
-        '#include "topopt_cuda.h"\\n#include <stdio.h>\\n'
-        "int main(void) {\\n"
-        "  int64_t nels[3] = {4, 2, 2}, nn, ne, nd, nz;\\n"
-        "  int rc = topopt_sizes(3, 3, nels, &nn, &ne, &nd, &nz);\\n"
-        '  printf("%d %lld %lld %lld %lld\\\\n", rc, (long long)nn, (long long)ne, (long long)nd, (long long)nz);\\n'
-        "  return rc;\\n}\\n"
-    )
+    src.write_text(C_PROGRAM)
     exe = tmp_path / "abi"
     libdir = os.path.join(ROOT, "topopt.jl_b200")
     cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
            "-L", libdir, "-ltopopt_cuda", f"-Wl,-rpath,{libdir}"]
-    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
     assert out == ["0", "45", "16", "135", "5733"]
