@@ -48,6 +48,12 @@ enum { TOPOPT_PENALTY_POWER = 0, TOPOPT_PENALTY_RATIONAL = 1, TOPOPT_PENALTY_SIN
 enum { TOPOPT_OP_MATRIX_FREE = 0, TOPOPT_OP_ASSEMBLED = 1 };
 /* preconditioner: identity or DiagonalPreconditioner (Preconditioners.jl, solvers_api.jl:187-192) */
 enum { TOPOPT_PRECOND_NONE = 0, TOPOPT_PRECOND_JACOBI = 1 };
+/* CG scalar recurrence.  REFERENCE reproduces IterativeSolvers 0.9 cg! iterate by iterate
+ * (three vector passes per iteration).  SINGLE_PASS is the same Krylov method with beta predicted
+ * from |r - alpha Ap|^2 = alpha^2 Ap.Ap - r.r, which lets x, r and p be updated in one pass; its
+ * iterates agree with the reference's to rounding (identity / default criteria only, otherwise
+ * the library falls back to REFERENCE). */
+enum { TOPOPT_CG_REFERENCE = 0, TOPOPT_CG_SINGLE_PASS = 1 };
 /* convergence criteria: src/FEA/convergence_criteria.jl:13-45 */
 enum { TOPOPT_CRITERIA_DEFAULT = 0, TOPOPT_CRITERIA_ENERGY = 1 };
 /* physics for topopt_element_matrix */
@@ -89,7 +95,11 @@ typedef struct {
   int32_t precond;        /* TOPOPT_PRECOND_*                                                    */
   int32_t criteria;       /* TOPOPT_CRITERIA_*                                                   */
   int32_t check_every;    /* host polls the device convergence flag every N iterations (0=auto) */
-  int32_t reserved;
+  int32_t variant;        /* TOPOPT_CG_*: scalar recurrence (0 = the reference's)                */
+  int32_t warm_start;     /* 0 = zero initial guess like the reference (solvers_api.jl:203);
+                             1 = start from the device-resident solution of the previous solve   */
+  int32_t refresh_precond;/* 0 = preconditioner built once per solver like the reference
+                             (solvers_api.jl:187-192); 1 = rebuild it from the current stiffness */
 } topopt_cg_opts;
 
 typedef struct {
@@ -168,6 +178,12 @@ int topopt_get_stiffness(topopt_handle* h, double* E, double* dE);
 /* mul!(y, MatrixFreeOperator, x)  (src/FEA/matrix_free_operator.jl:66-105) */
 int topopt_apply(topopt_handle* h, const double* x, double* y);
 
+/* The same product through ONE kernel generation, with the dot products that kernel fuses for the
+ * CG loop: kernel 0 = what topopt_apply selects, 1 = dense node-centric gather, 2 = hex8 modal
+ * one-row, 3 = hex8 modal two-row, 4 = hex8 ring-staged (requires x == 0 on prescribed dofs, as
+ * every CG direction is).  dots (2 doubles, may be NULL): x.y and, for kernel 4, y.y. */
+int topopt_apply_ex(topopt_handle* h, const double* x, double* y, int32_t kernel, double* dots);
+
 /* assemble!(globalinfo, ...) + apply!  (src/TopOptProblems/assemble.jl:28-90).  nzval (nnz, in
  * the order of topopt_csc_pattern) and f (ndof) may be NULL. */
 int topopt_assemble(topopt_handle* h, double* nzval, double* f);
@@ -217,8 +233,11 @@ int topopt_simp_eval(topopt_handle* h, topopt_filter* f, int32_t filter_kind, co
 
 /* ---- measurement ---------------------------------------------------------------------- */
 /* time `reps` back-to-back launches of one kernel class with CUDA events on the library's
- * stream; which: 0 = K.u matrix-free, 1 = CG iteration (matrix-free), 2 = sensitivity,
- * 3 = filter forward, 4 = SpMV, 5 = assembly, 6 = CG iteration (assembled).  ms = average per rep. */
+ * stream; which: 0 = K.u as the CG loop launches it (dense direction vector, fused p.Ap),
+ * 1 = CG iteration (matrix-free, reference recurrence), 2 = sensitivity, 3 = filter forward,
+ * 4 = SpMV, 5 = assembly, 6 = CG iteration (assembled), 7 = K.u, previous-generation shuffle
+ * kernels, 8 = K.u ring-staged with p.Ap and Ap.Ap, 9 = CG iteration (single-pass recurrence).
+ * ms = average per rep. */
 int topopt_time_kernel(topopt_handle* h, topopt_filter* f, int32_t which, int32_t reps,
                        double* ms);
 

@@ -1,0 +1,248 @@
+"""GPU parity tests of the kernel generations that ship for the large 3-D configurations, driven one by
+one through the C ABI (topopt_apply_ex) against the CPU oracle, plus the CG variants built on them.
+
+* every hex8 K.u generation (dense gather, modal one-row, modal two-row, ring-staged) on grids that are
+  tall enough for the two-row / ring kernels to be the ones the library selects (>= 96 node planes),
+  span several tiles in x and y, have ragged last tiles and odd / even node counts (bulk-copy alignment);
+* the dot products each kernel fuses for CG;
+* CG iterate parity with the reference recurrence THROUGH the selected kernels, and the single-pass
+  recurrence against the reference recurrence;
+* BASELINE config 4 (256x128x128, 12.8 M dofs) at full size against the OpenMP C port of the
+  reference CPU path: K.u <= 1e-12, ten CG iterates <= 1e-10.
+
+Reference: src/FEA/matrix_free_operator.jl:66-105, IterativeSolvers 0.9 cg!.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import topopt_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+RTOL_OP = 1e-12
+KERNELS = {"dense": 1, "one_row": 2, "two_row": 3, "ring": 4}
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300))
+
+
+def rand_rho(n, seed=42):
+    return np.random.default_rng(seed).uniform(0.2, 1.0, n)
+
+
+def masked_x(oprob, seed):
+    x = np.random.default_rng(seed).standard_normal(oprob.ndof)
+    x[oprob.prescribed] = 0.0
+    return x
+
+
+def make(t, nels, sizes=None, **kw):
+    args = (nels,) if sizes is None else (nels, sizes)
+    prob, oprob = t.PointLoadCantilever(*args), o.PointLoadCantilever(*args)
+    prob.Ke = oprob.Ke.copy()
+    kw.setdefault("penalty", t.PowerPenaltyFun(3.0))
+    return prob, oprob, t.FEASolver(t.CUDAMatrixFreeSolver, prob, **kw)
+
+
+# nown >= 96 selects the two-row kernel in topopt_apply and nown >= 24 the ring kernel inside CG
+TALL_GRIDS = [
+    (8, 4, 100),      # one tile, thin and tall
+    (33, 24, 100),    # 2 x 2 tiles, ragged, NX even / NY odd
+    (64, 47, 97),     # 3 x 3 tiles (ring: 31-column, 23-row tiles), NX odd
+    (30, 22, 26),     # exactly one ring tile of owned nodes + 1
+    (62, 23, 25),     # tile boundaries fall on the last node column / row
+]
+
+
+@pytest.mark.parametrize("nels", TALL_GRIDS)
+@pytest.mark.parametrize("kernel", list(KERNELS))
+def test_hex8_kernel_generations_match_reference_operator(lib, nels, kernel):
+    t = lib
+    prob, oprob, s = make(t, nels)
+    rho = rand_rho(prob.nel, 5)
+    E = o.get_rho(rho, 3.0, 1e-3)
+    s.set_density(rho)
+    x = masked_x(oprob, 3)
+    yref = o.matfree_mul(oprob, E, x)
+    y, xy, yy = s.mul_ex(x, KERNELS[kernel])
+    assert rel(y, yref) < RTOL_OP
+    assert abs(xy - float(x @ yref)) <= 1e-11 * float(np.abs(x) @ np.abs(yref))
+    if kernel == "ring":
+        assert abs(yy - float(yref @ yref)) <= 1e-11 * float(yref @ yref)
+    # bitwise run-to-run reproducibility (fixed summation order, no atomics on the data path)
+    y2, xy2, yy2 = s.mul_ex(x, KERNELS[kernel])
+    assert np.array_equal(y, y2) and xy == xy2 and yy == yy2
+    s.close()
+
+
+def test_ring_kernel_noncubic_cells_and_default_selection(lib):
+    """Non-cubic cells change every modal coefficient; topopt_apply (kernel 0) on >= 96 planes is the
+    two-row kernel and must agree with the ring kernel on a premasked vector to rounding."""
+    t = lib
+    prob, oprob, s = make(t, (20, 9, 98), (1.0, 0.5, 2.0))
+    rho = rand_rho(prob.nel, 8)
+    s.set_density(rho)
+    E = o.get_rho(rho, 3.0, 1e-3)
+    x = masked_x(oprob, 13)
+    yref = o.matfree_mul(oprob, E, x)
+    for k in (0, 3, 4):
+        y, _, _ = s.mul_ex(x, k)
+        assert rel(y, yref) < RTOL_OP
+    # arbitrary (unmasked) x through the default path: bcmatrix column masking + meandiag rows
+    xr = np.random.default_rng(2).standard_normal(oprob.ndof)
+    assert rel(s.mul(xr), o.matfree_mul(oprob, E, xr)) < RTOL_OP
+    s.close()
+
+
+@pytest.mark.parametrize("nels", [(12, 7, 30), (33, 24, 100)])
+def test_cg_iterates_through_shipped_kernels(lib, nels):
+    """IterativeSolvers' recurrence through the kernels the library selects on tall grids (ring-staged
+    K.u with the fused p.Ap): same iterates as the oracle's cg! for 1 / 5 / 20 iterations."""
+    t = lib
+    prob, oprob, s0 = make(t, nels)
+    s0.close()
+    rho = rand_rho(prob.nel)
+    E = o.get_rho(rho, 3.0, 1e-3)
+    for maxiter in (1, 5, 20):
+        s = t.FEASolver(t.CUDAMatrixFreeSolver, prob, penalty=t.PowerPenaltyFun(3.0), cg_max_iter=maxiter, abstol=0.0, reltol=0.0)
+        s.vars = rho
+        u = s().copy()
+        uref, it, res = o.solve_matfree(oprob, E, abstol=0.0, reltol=0.0, maxiter=maxiter)
+        assert s.last_result.iters == it == maxiter
+        assert abs(s.last_result.residual - res) <= 1e-9 * res
+        assert rel(u, uref) < (1e-12 if maxiter <= 5 else 1e-7)
+        s.close()
+
+
+@pytest.mark.parametrize("nels", [(12, 7, 30), (40, 25, 50)])
+def test_single_pass_cg_matches_reference_recurrence(lib, nels):
+    """TOPOPT_CG_SINGLE_PASS: beta predicted from alpha^2 Ap.Ap - r.r, one fused vector pass.  Same
+    Krylov method: iterates agree with the reference recurrence to rounding for short runs, the converged
+    solution / compliance / sensitivities to the solve tolerance, iteration counts within a few."""
+    t = lib
+    prob, oprob, s0 = make(t, nels)
+    s0.close()
+    rho = rand_rho(prob.nel, 21)
+    mk = lambda variant, **kw: t.FEASolver(t.CUDAMatrixFreeSolver, prob, penalty=t.PowerPenaltyFun(3.0), cg_variant=variant, **kw)
+    for maxiter in (1, 5, 20):
+        a, b = mk(0, cg_max_iter=maxiter, abstol=0.0, reltol=0.0), mk(1, cg_max_iter=maxiter, abstol=0.0, reltol=0.0)
+        a.vars = rho
+        b.vars = rho
+        ua, ub = a().copy(), b().copy()
+        assert a.last_result.iters == b.last_result.iters == maxiter
+        assert rel(ub, ua) < (1e-12 if maxiter <= 5 else 1e-8)
+        assert abs(a.last_result.residual - b.last_result.residual) <= 1e-8 * a.last_result.residual
+        a.close()
+        b.close()
+    a, b = mk(0, abstol=1e-10, reltol=0.0, cg_max_iter=20000), mk(1, abstol=1e-10, reltol=0.0, cg_max_iter=20000)
+    ca, cb = t.ComplianceFun(a), t.ComplianceFun(b)
+    va, ga = ca.value_and_grad(rho)
+    vb, gb = cb.value_and_grad(rho)
+    assert a.last_result.converged == 1 and b.last_result.converged == 1
+    assert abs(a.last_result.iters - b.last_result.iters) <= max(3, a.last_result.iters // 20)
+    assert abs(va - vb) / va < 1e-8 and rel(gb, ga) < 1e-8 and rel(b.u, a.u) < 1e-7
+    if oprob.nel < 3000:
+        uref = o.solve_direct(oprob, o.get_rho(rho, 3.0, 1e-3))
+        obj, _, g = o.compliance(oprob, uref, rho, 3.0, 1e-3)
+        assert abs(vb - obj) / obj < 1e-8 and rel(gb, g) < 1e-8
+    a.close()
+    b.close()
+
+
+def test_warm_start_and_refreshed_jacobi(lib):
+    """Opt-in extensions over the reference (solvers_api.jl:187-203): warm start from the resident solution
+    and a Jacobi preconditioner rebuilt from the current stiffness reach the same solution in fewer
+    iterations; the defaults (zero start, stale preconditioner) are unchanged."""
+    t = lib
+    prob, oprob, s = make(t, (16, 8, 30), abstol=1e-10, reltol=0.0, cg_max_iter=20000)
+    rho1, rho2 = rand_rho(prob.nel, 1), rand_rho(prob.nel, 1) * 0.98 + 0.01
+    s.vars = rho1
+    s()
+    s.vars = rho2
+    u_cold = s().copy()
+    it_cold = s.last_result.iters
+    w = t.FEASolver(t.CUDAMatrixFreeSolver, prob, penalty=t.PowerPenaltyFun(3.0), abstol=1e-10, reltol=0.0, cg_max_iter=20000, warm_start=True)
+    w.vars = rho1
+    w()
+    w.vars = rho2
+    u_warm = w().copy()
+    assert w.last_result.converged == 1 and w.last_result.iters < it_cold
+    assert rel(u_warm, u_cold) < 1e-7
+    uref = o.solve_direct(oprob, o.get_rho(rho2, 3.0, 1e-3))
+    assert rel(u_warm, uref) < 1e-7
+    # refreshed Jacobi: same solution as the oracle's direct solve, fewer iterations than the stale one
+    j0 = t.FEASolver(t.CUDAMatrixFreeSolver, prob, penalty=t.PowerPenaltyFun(3.0), abstol=1e-10, reltol=0.0, cg_max_iter=20000, preconditioner="jacobi")
+    j1 = t.FEASolver(t.CUDAMatrixFreeSolver, prob, penalty=t.PowerPenaltyFun(3.0), abstol=1e-10, reltol=0.0, cg_max_iter=20000, preconditioner="jacobi",
+                     refresh_preconditioner=True)
+    for j in (j0, j1):
+        j.vars = np.full(prob.nel, 0.5)
+        j()  # the reference builds the preconditioner here, once
+        j.vars = rho2
+        j()
+        assert j.last_result.converged == 1
+        assert rel(j.u, uref) < 1e-7
+    assert j1.last_result.iters <= j0.last_result.iters
+    for q in (s, w, j0, j1):
+        q.close()
+
+
+def test_graph_cache_survives_solution_swap(lib):
+    """the CUDA-graph cache key must cover every buffer baked into the captured launches.
+    solve(rhs) -> swap -> solve(rhs) with several graph batches per solve must still match the oracle."""
+    t = lib
+    prob, oprob, s = make(t, (10, 4, 6), abstol=1e-12, reltol=1e-14, cg_max_iter=5000, check_every=5)
+    rho = rand_rho(prob.nel, 4)
+    E = o.get_rho(rho, 3.0, 1e-3)
+    s.vars = rho
+    rhs = np.random.default_rng(9).standard_normal(prob.ndof)
+    uref = o.solve_direct(oprob, E, rhs=rhs)
+    for k in range(3):
+        out = np.zeros(prob.ndof)
+        s(rhs=rhs, lhs=out)
+        assert s.last_result.converged == 1 and s.last_result.iters > 10
+        assert rel(out, uref) < 1e-8
+        s._check(s._lib.topopt_swap_solution_lambda(s.handle))
+    s.close()
+
+
+@pytest.mark.skipif(os.environ.get("TOPOPT_SKIP_FULL_SIZE") == "1", reason="full-size config 4 disabled")
+def test_config4_full_size_against_c_port(lib):
+    """BASELINE config 4 at full size (256x128x128 hex8, 12 830 211 dofs), the OpenMP C port of the
+    reference CPU path as the checker: K.u through every shipped kernel <= 1e-12, ten CG iterates of
+    both recurrences <= 1e-10 (relative to max|u|), residual norms <= 1e-9."""
+    import ref_c
+
+    t = lib
+    nels = (256, 128, 128)
+    prob = t.PointLoadCantilever(nels)
+    R = ref_c.RefProblem(3, 3, nels, prob.Ke, prob.prescribed_dofs, openmp=True, native=True)
+    nel = prob.nel
+    # SURVEY 8d density field (B): deterministic, cheap to build at 4.2 M elements
+    rho = 0.2 + 0.8 * ((np.arange(nel, dtype=np.int64) * 2654435761 % 1000003) / 1000003.0)
+    R.set_density(rho, 3.0, 1e-3)
+    s = t.FEASolver(t.CUDAMatrixFreeSolver, prob, penalty=t.PowerPenaltyFun(3.0), cg_max_iter=10, abstol=0.0, reltol=0.0)
+    s.set_density(rho)
+    x = np.random.default_rng(7).standard_normal(prob.ndof)
+    x[prob.prescribed_dofs - 1] = 0.0
+    yref = R.mul(x)
+    for k in (0, 2, 3, 4):
+        y, xy, _ = s.mul_ex(x, k)
+        assert rel(y, yref) < RTOL_OP, f"kernel {k}"
+        assert abs(xy - float(x @ yref)) <= 1e-10 * float(np.abs(x) @ np.abs(yref))
+    b = prob.fixedload.copy()
+    b[prob.prescribed_dofs - 1] = 0.0
+    uref, it, res = R.cg(b, abstol=0.0, reltol=0.0, maxiter=10)
+    assert it == 10
+    for variant in (0, 1):
+        s.cg_variant = variant
+        s.vars = rho
+        u = s().copy()
+        assert s.last_result.iters == 10
+        assert rel(u, uref) < 1e-10
+        assert abs(s.last_result.residual - res) <= 1e-9 * res
+    R.close()
+    s.close()

@@ -19,6 +19,7 @@ PENALTY_POWER, PENALTY_RATIONAL, PENALTY_SINH = 0, 1, 2
 OP_MATRIX_FREE, OP_ASSEMBLED = 0, 1
 PRECOND_NONE, PRECOND_JACOBI = 0, 1
 CRITERIA_DEFAULT, CRITERIA_ENERGY = 0, 1
+CG_REFERENCE, CG_SINGLE_PASS = 0, 1
 PHYSICS_ELASTICITY, PHYSICS_HEAT = 0, 1
 FILTER_FORWARD, FILTER_TRANSPOSE = 0, 1
 
@@ -55,7 +56,9 @@ class CGOpts(C.Structure):
         ("precond", C.c_int32),
         ("criteria", C.c_int32),
         ("check_every", C.c_int32),
-        ("reserved", C.c_int32),
+        ("variant", C.c_int32),
+        ("warm_start", C.c_int32),
+        ("refresh_precond", C.c_int32),
     ]
 
 
@@ -111,6 +114,7 @@ SIGNATURES = {
     "topopt_set_stiffness": (C.c_int, [VP, VP, VP]),
     "topopt_get_stiffness": (C.c_int, [VP, VP, VP]),
     "topopt_apply": (C.c_int, [VP, VP, VP]),
+    "topopt_apply_ex": (C.c_int, [VP, VP, VP, C.c_int32, c_dp]),
     "topopt_assemble": (C.c_int, [VP, VP, VP]),
     "topopt_spmv": (C.c_int, [VP, VP, VP]),
     "topopt_set_jacobi": (C.c_int, [VP, VP]),

@@ -19,6 +19,7 @@
 #include "kernels.cuh"
 #include "kxu_hex8.cuh"
 #include "kxu_hex8_2row.cuh"
+#include "kxu_hex8_ring.cuh"
 
 using namespace topopt;
 
@@ -79,6 +80,9 @@ struct topopt_handle {
   double Kh[48];          // modal coefficients (hex8 elasticity fast path)
   bool modal_ok = false;  // Ke has the brick/isotropic modal sparsity pattern
   int kxu_ty = 16, kxu_waves = 1, kxu_nsync = 1, kxu_2row = 1;  // 2row: 0 = one-row kernel, 1 = auto, else thread rows
+  int kxu_ring = 1;       // ring-staged kernel for premasked inputs (CG directions): 0 = off, 1 = auto, else thread rows
+  int kxu_ring_min = 24;  // fewest owned node planes per rank for which the ring kernel is selected
+  int cg_variant_env = -1;  // TOPOPT_CG_VARIANT overrides topopt_cg_opts.variant (diagnostics)
   double fixed_diag = 0.0, cellvol = 1.0;
   double sizes[3] = {1, 1, 1};
   // device buffers
@@ -96,6 +100,7 @@ struct topopt_handle {
   // CUDA-graph cache for one batch of CG iterations (same kernel arguments every batch)
   cudaGraphExec_t cg_graph = nullptr;
   unsigned long long cg_graph_key = 0;
+  long long cg_graph_launches = 0;
   bool use_graphs = true;
   bool no_fuse = true;  // fusing p = r + beta p into K.u measured slower (LSU-bound kernel); opt in with TOPOPT_FUSE_P=1
   double *d_D = nullptr, *d_rhs = nullptr, *d_lam = nullptr, *d_tmp = nullptr;
@@ -308,6 +313,16 @@ int sync(topopt_handle* h) {
 // ---- operator application -----------------------------------------------------------------
 constexpr int kMaxPartialBlocks = 16384;
 
+// cudaFuncSetAttribute is per device: one bit per device ordinal for every kernel instantiation
+template <typename K>
+int ensure_dyn_smem(topopt_handle* h, K kernel, size_t smem, std::atomic<unsigned long long>& mask) {
+  const unsigned long long bit = 1ull << (h->device & 63);
+  if (mask.load(std::memory_order_acquire) & bit) return TOPOPT_OK;
+  CUDA_TRY(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mask.fetch_or(bit, std::memory_order_release);
+  return TOPOPT_OK;
+}
+
 template <int TY, bool DOT, bool FUSEP, bool PEER, bool NSYNC>
 int launch_hex8_modal(topopt_handle* h, const double* x, double* y, int fin, const double* r, double* pnew) {
   const Geo& g = h->g;
@@ -319,11 +334,8 @@ int launch_hex8_modal(topopt_handle* h, const double* x, double* y, int fin, con
   if (grid > units) grid = (int)units;
   if (grid > kMaxPartialBlocks) grid = kMaxPartialBlocks;
   const size_t smem = sizeof(double) * 2 * 12 * TY * 32;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
-    CUDA_TRY(h, cudaFuncSetAttribute(k_apply_hex8_modal<TY, DOT, FUSEP, PEER, NSYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_mask{0};  // per template instantiation, one bit per device
+  TRY(ensure_dyn_smem(h, k_apply_hex8_modal<TY, DOT, FUSEP, PEER, NSYNC>, smem, attr_mask));
   const double* xlo = nullptr;
   const double* xhi = nullptr;
   if (PEER) {  // neighbours' boundary planes of the same buffer (d_p), read over NVLink
@@ -345,11 +357,8 @@ int launch_hex8_modal2(topopt_handle* h, const double* x, double* y, int fin) {
   const long long units = (long long)tilesX * tilesY * g.nown;
   if (grid > units) grid = (int)units;
   const size_t smem = sizeof(double) * 2 * 12 * TYT * 32;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(h, cudaFuncSetAttribute(k_apply_hex8_modal2<TYT, DOT, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_mask{0};
+  TRY(ensure_dyn_smem(h, k_apply_hex8_modal2<TYT, DOT, PEER>, smem, attr_mask));
   const double* xlo = nullptr;
   const double* xhi = nullptr;
   if (PEER) {
@@ -360,6 +369,62 @@ int launch_hex8_modal2(topopt_handle* h, const double* x, double* y, int fin) {
                                                                           h->d_partials, h->d_st, fin, xlo, xhi);
   h->stats.kernel_launches += 1;
   return check_launch(h, "k_apply_hex8_modal2");
+}
+
+// Ring-staged kernel (kxu_hex8_ring.cuh).  x must be zero on prescribed dofs.
+template <int TYT, int DOT, bool PEER>
+int launch_hex8_ring_t(topopt_handle* h, const double* x, double* y, int fin) {
+  constexpr int NST = 4;
+  const Geo& g = h->g;
+  constexpr int OWNR = 2 * TYT - 1;
+  const int tilesX = (g.NX + 30) / 31, tilesY = (g.NY + OWNR - 1) / OWNR;
+  int grid = 148 * std::max(1, h->kxu_waves);
+  const long long units = (long long)tilesX * tilesY * g.nown;
+  if (grid > units) grid = (int)units;
+  const size_t smem = (size_t)NST * (2 * TYT + 1) * kRingPitch + sizeof(double) * 2 * 6 * TYT * 32;
+  static std::atomic<unsigned long long> attr_mask{0};
+  TRY(ensure_dyn_smem(h, k_apply_hex8_ring<TYT, NST, DOT, PEER>, smem, attr_mask));
+  const double* xlo = nullptr;
+  const double* xhi = nullptr;
+  if (PEER) {
+    if (h->peer_p_lo) xlo = h->peer_p_lo + (size_t)h->plane_dofs * h->nown_lower;
+    if (h->peer_p_hi) xhi = h->peer_p_hi + (size_t)h->plane_dofs;
+  }
+  k_apply_hex8_ring<TYT, NST, DOT, PEER><<<grid, 32 * TYT, smem, h->stream>>>(g, x, y, h->d_E, h->d_fixed, h->fixed_diag, tilesX, tilesY,
+                                                                             h->d_partials, h->d_st, fin, xlo, xhi);
+  h->stats.kernel_launches += 1;
+  return check_launch(h, "k_apply_hex8_ring");
+}
+
+// thread rows per CTA of the ring kernel: fewest wasted node rows for this grid (a tile owns 2*TYT-1 rows)
+inline int ring_rows(const topopt_handle* h) {
+  if (h->kxu_ring > 1) return h->kxu_ring;
+  double best = -1.0;
+  int tyt = 12;
+  const int cand[3] = {12, 10, 8};
+  for (int k = 0; k < 3; ++k) {
+    const int own = 2 * cand[k] - 1;
+    const int tiles = (h->g.NY + own - 1) / own;
+    const double eff = (double)h->g.NY / ((double)tiles * 2 * cand[k]);
+    if (eff > best + 1e-9) {
+      best = eff;
+      tyt = cand[k];
+    }
+  }
+  return tyt;
+}
+
+inline bool use_ring(const topopt_handle* h) {
+  return h->kxu_ring != 0 && h->dim == 3 && h->nc == 3 && h->modal_ok && h->g.nown >= h->kxu_ring_min;
+}
+
+template <int DOT, bool PEER>
+int launch_hex8_ring(topopt_handle* h, const double* x, double* y, int fin) {
+  switch (ring_rows(h)) {
+    case 8: return launch_hex8_ring_t<8, DOT, PEER>(h, x, y, fin);
+    case 10: return launch_hex8_ring_t<10, DOT, PEER>(h, x, y, fin);
+    default: return launch_hex8_ring_t<12, DOT, PEER>(h, x, y, fin);
+  }
 }
 
 template <bool DOT, bool FUSEP, bool PEER = false>
@@ -426,7 +491,23 @@ int launch_spmv(topopt_handle* h, const double* x, double* y, int fin) {
 int build_pattern(topopt_handle* h);
 int do_assemble(topopt_handle* h);
 
-// IterativeSolvers cg! with x0 = 0: see cg_finalize() for the scalar recurrences.
+// K.u inside the CG loop: the direction vector is zero on prescribed dofs, so the ring-staged kernel
+// applies; DOT = 1 reduces p.Ap, DOT = 2 also Ap.Ap (single-pass recurrence).
+template <int DOT>
+int launch_cg_apply(topopt_handle* h, bool peer_halo, int fin) {
+  const bool hex8 = h->dim == 3 && h->nc == 3 && h->modal_ok;
+  if (hex8 && use_ring(h)) {
+    if (peer_halo) return launch_hex8_ring<DOT, true>(h, h->d_p, h->d_Ap, fin);
+    TRY(exchange_halo(h, h->d_p));
+    return launch_hex8_ring<DOT, false>(h, h->d_p, h->d_Ap, fin);
+  }
+  if (DOT == 2) return fail(h, TOPOPT_ERR_INVALID, "single-pass CG needs the ring-staged hex8 kernel");
+  if (peer_halo) return launch_hex8<true, false, true>(h, h->d_p, h->d_Ap, fin, nullptr, nullptr);
+  TRY(exchange_halo(h, h->d_p));
+  return launch_apply<true>(h, h->d_p, h->d_Ap, fin);
+}
+
+// IterativeSolvers cg!: see cg_finalize() for the scalar recurrences.
 // b (local layout) must already be zero on prescribed dofs.
 int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_cg_result* res, bool ignore_convergence = false,
              int fixed_iters = 0) {
@@ -436,8 +517,21 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
     if (!h->assembled || h->stiffness_dirty) TRY(do_assemble(h));
   }
   const bool pre = o->precond == TOPOPT_PRECOND_JACOBI;
+  if (pre && o->refresh_precond) {
+#define CALL(D, C) LAUNCH(h, (k_diag<D, C>), grid_for((long long)h->g.S * h->g.nown, kWideGrid), h->g, h->d_D, h->d_E, h->d_fixed, h->fixed_diag)
+    DISPATCH(h, CALL);
+#undef CALL
+    TRY(check_launch(h, "k_diag"));
+    h->have_jacobi = true;
+  }
   if (pre && !h->have_jacobi) return fail(h, TOPOPT_ERR_INVALID, "Jacobi preconditioner requested but topopt_set_jacobi was not called");
   const bool energy = o->criteria == TOPOPT_CRITERIA_ENERGY;
+  const bool peer = h->world > 1 && h->peer_ready;                       // in-kernel allreduce over peer memory
+  const bool hex8 = !assembled && h->dim == 3 && h->nc == 3 && h->modal_ok;
+  const bool peer_halo = peer && hex8;  // + direct halo reads
+  // single-pass recurrence: identity preconditioner, default criteria, ring-staged K.u, device-side scalars
+  int want_variant = h->cg_variant_env >= 0 ? h->cg_variant_env : o->variant;
+  const bool single = want_variant == TOPOPT_CG_SINGLE_PASS && !pre && !energy && hex8 && use_ring(h) && (h->world == 1 || peer);
   CGState& s = *h->h_st;
   std::memset(&s, 0, sizeof(CGState));
   s.abstol = ignore_convergence ? -1.0 : o->abstol;
@@ -446,15 +540,27 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
   s.criteria = ignore_convergence ? 0 : o->criteria;
   s.precond = pre ? 1 : 0;
   s.world = h->world;
-  const bool peer = h->world > 1 && h->peer_ready;                       // in-kernel allreduce over peer memory
-  const bool peer_halo = peer && !assembled && h->dim == 3 && h->nc == 3 && h->modal_ok;  // + direct halo reads
+  s.variant = single ? 1 : 0;
   s.peer = peer ? h->d_peercomm : nullptr;
   CUDA_TRY(h, cudaMemcpyAsync(h->d_st, &s, sizeof(CGState), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
   const double* D = pre ? h->d_D : nullptr;
   // vector kernels: 4 elements per thread and trip; small problems get a proportionally small grid
   const int vgrid = (int)std::min<long long>(kReduceBlocks, std::max<long long>(1, (h->nown_dofs + 4 * kBlock - 1) / (4 * kBlock)));
-  LAUNCH(h, k_cg_init, vgrid, h->off, h->nown_dofs, b, h->d_u, h->d_r, h->d_p, D, h->d_partials, h->d_st);
+  const double* b0 = b;
+  if (o->warm_start) {
+    // r0 = b - K u_prev (u_prev is zero on prescribed dofs: it came out of a CG solve); the ghost planes of
+    // d_u were refreshed at the end of that solve
+    if (assembled) {
+      TRY(launch_spmv<false>(h, h->d_u, h->d_Ap, FIN_NONE));
+    } else {
+      TRY(launch_apply<false>(h, h->d_u, h->d_Ap, FIN_NONE));
+    }
+    LAUNCH(h, k_axpby, vgrid, h->off, h->nown_dofs, 1.0, b, -1.0, h->d_Ap, h->d_tmp);
+    b0 = h->d_tmp;
+  }
+  LAUNCH(h, k_cg_init, vgrid, h->off, h->nown_dofs, b0, o->warm_start ? (double*)nullptr : h->d_u, h->d_r, h->d_p, D, h->d_partials,
+         h->d_st, single ? 1 : 0, (single && peer_halo) ? 1 : 0);
   TRY(check_launch(h, "k_cg_init"));
   if (h->world > 1 && !peer) {
     TRY(allreduce_sums(h, 2));
@@ -469,7 +575,7 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (h->h_st->done || issued >= maxiter) break;
     const int n = std::min(batch, maxiter - issued);
-    const bool fusep = !assembled && !pre && h->world == 1 && h->dim == 3 && h->nc == 3 && h->modal_ok && !h->no_fuse;
+    const bool fusep = !single && !assembled && !pre && h->world == 1 && hex8 && !h->no_fuse && !use_ring(h);
     // TOPOPT_TRACE=1: per-phase device times of the first batch (diagnostic, perturbs the run)
     static const bool trace = getenv("TOPOPT_TRACE") != nullptr;
     std::vector<cudaEvent_t> tev;
@@ -480,24 +586,33 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
       cudaEventRecord(e, h->stream);
       tev.push_back(e);
     };
+    int launches_per_iter = 0;
     auto one_iteration = [&]() -> int {
+      launches_per_iter = 0;
       mark();
+      if (single) {  // K.u (+ p.Ap, Ap.Ap -> alpha, beta) ; x, r, p in one pass (+ r.r)
+        TRY(launch_cg_apply<2>(h, peer_halo, FIN_PAP2));
+        mark();
+        LAUNCH(h, k_update_xrp, vgrid, h->off, h->nown_dofs, h->d_u, h->d_r, h->d_p, h->d_Ap, h->d_partials, h->d_st, peer_halo ? 1 : 0);
+        launches_per_iter = 2;
+        return TOPOPT_OK;
+      }
       if (fusep) {  // p_new = r + beta p_old formed inside the K.u kernel
         TRY((launch_hex8<true, true>(h, h->d_p, h->d_Ap, FIN_PAP, h->d_r, h->d_p2)));
         std::swap(h->d_p, h->d_p2);
       } else {
-      LAUNCH(h, k_update_p, vgrid, h->off, h->nown_dofs, h->d_r, h->d_p, D, h->d_st, peer_halo ? 1 : 0);
-      if (assembled) {
-        TRY(launch_spmv<true>(h, h->d_p, h->d_Ap, FIN_PAP));
-      } else {
-        if (peer_halo) {
-          mark();
-          TRY((launch_hex8<true, false, true>(h, h->d_p, h->d_Ap, FIN_PAP, nullptr, nullptr)));
+        LAUNCH(h, k_update_p, vgrid, h->off, h->nown_dofs, h->d_r, h->d_p, D, h->d_st, peer_halo ? 1 : 0);
+        if (assembled) {
+          TRY(launch_spmv<true>(h, h->d_p, h->d_Ap, FIN_PAP));
         } else {
-          TRY(exchange_halo(h, h->d_p));
-          TRY(launch_apply<true>(h, h->d_p, h->d_Ap, FIN_PAP));
+          mark();
+          if (hex8) {
+            TRY(launch_cg_apply<1>(h, peer_halo, FIN_PAP));
+          } else {
+            TRY(exchange_halo(h, h->d_p));
+            TRY(launch_apply<true>(h, h->d_p, h->d_Ap, FIN_PAP));
+          }
         }
-      }
       }
       if (h->world > 1 && !peer) {
         TRY(allreduce_sums(h, 1));
@@ -516,19 +631,22 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
         k_finalize<<<1, 1, 0, h->stream>>>(h->d_st, FIN_RR);
         h->stats.kernel_launches += 1;
       }
+      launches_per_iter = 3;
       return TOPOPT_OK;
     };
     // Replay a captured graph of n iterations when nothing in the batch depends on host state:
     // single GPU or the peer-memory path (no NCCL calls inside), no fused pointer swap, no tracing.
     const bool graphable = h->use_graphs && !trace && !fusep && (h->world == 1 || (peer && (peer_halo || assembled))) && issued > 0;
     if (graphable) {
+      // every pointer and flag baked into the captured launches is part of the key
       unsigned long long key = 1469598103934665603ULL;
       auto mix = [&](unsigned long long v) { key = (key ^ v) * 1099511628211ULL; };
-      mix((unsigned long long)(uintptr_t)b);
-      mix((unsigned long long)(uintptr_t)D);
-      mix((unsigned long long)(uintptr_t)h->d_p);
+      for (const void* q : {(const void*)b, (const void*)D, (const void*)h->d_p, (const void*)h->d_u, (const void*)h->d_r,
+                            (const void*)h->d_Ap, (const void*)h->d_E, (const void*)h->d_st})
+        mix((unsigned long long)(uintptr_t)q);
       mix((unsigned long long)n);
-      mix((unsigned long long)(energy ? 1 : 0) | (assembled ? 2 : 0) | (peer_halo ? 4 : 0) | (peer ? 8 : 0));
+      mix((unsigned long long)(energy ? 1 : 0) | (assembled ? 2 : 0) | (peer_halo ? 4 : 0) | (peer ? 8 : 0) | (single ? 16 : 0) |
+          (use_ring(h) ? 32 : 0) | ((unsigned long long)ring_rows(h) << 8));
       if (h->cg_graph == nullptr || h->cg_graph_key != key) {
         if (h->cg_graph) {
           cudaGraphExecDestroy(h->cg_graph);
@@ -554,12 +672,13 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
             for (int it = 0; it < n; ++it) TRY(one_iteration());
           } else {
             h->cg_graph_key = key;
+            h->cg_graph_launches = (long long)n * launches_per_iter;
             CUDA_TRY(h, cudaGraphLaunch(h->cg_graph, h->stream));
           }
         }
       } else {
         CUDA_TRY(h, cudaGraphLaunch(h->cg_graph, h->stream));
-        h->stats.kernel_launches += (long long)n * (assembled || !peer_halo ? 3 : 3);
+        h->stats.kernel_launches += h->cg_graph_launches;
       }
     } else {
       for (int it = 0; it < n; ++it) TRY(one_iteration());
@@ -892,7 +1011,10 @@ int topopt_create(const topopt_desc* d, topopt_handle** out) {
     if (const char* e = getenv("TOPOPT_KXU_WAVES")) h->kxu_waves = atoi(e);
     if (const char* e = getenv("TOPOPT_KXU_NSYNC")) h->kxu_nsync = atoi(e);
     if (const char* e = getenv("TOPOPT_KXU_2ROW")) h->kxu_2row = atoi(e);
+    if (const char* e = getenv("TOPOPT_KXU_RING")) h->kxu_ring = atoi(e);
+    if (const char* e = getenv("TOPOPT_KXU_RING_MIN")) h->kxu_ring_min = atoi(e);
   }
+  if (const char* e = getenv("TOPOPT_CG_VARIANT")) h->cg_variant_env = atoi(e);
 
   // slab partition along the last axis
   const int NLg = (int)(h->dim == 3 ? gd.nz : gd.ny);
@@ -979,7 +1101,7 @@ int topopt_create(const topopt_desc* d, topopt_handle** out) {
   CTRY(dev_alloc(h, &h->d_block, h->nloc_nodes));
   CTRY(dev_alloc(h, &h->d_fixed, h->nloc_nodes));
   for (double** v : {&h->d_b, &h->d_fload, &h->d_u, &h->d_r, &h->d_p, &h->d_p2, &h->d_Ap, &h->d_D, &h->d_rhs, &h->d_lam, &h->d_tmp})
-    CTRY(dev_alloc(h, v, h->nloc_dofs));
+    CTRY(dev_alloc(h, v, h->nloc_dofs + 4));  // + 32 bytes: 16-byte aligned bulk copies may over-read a row end
   for (double** v : {&h->d_E, &h->d_dE, &h->d_rho, &h->d_cell, &h->d_grad}) CTRY(dev_alloc(h, v, h->nloc_el));
   CTRY(dev_alloc(h, &h->d_full_dof, h->ndof));
   for (double** v : {&h->d_full_el, &h->d_design, &h->d_xf, &h->d_gfull}) CTRY(dev_alloc(h, v, h->nel));
@@ -1122,6 +1244,50 @@ int topopt_apply(topopt_handle* h, const double* x, double* y) {
   CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
   if (y) TRY(download_dofs(h, h->d_Ap, y));
   TRY(sync(h));
+  float ms = 0;
+  CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->stats.last_apply_ms = ms;
+  return TOPOPT_OK;
+}
+
+// topopt_apply through one specific kernel generation, with the fused dot products the CG loop uses
+int topopt_apply_ex(topopt_handle* h, const double* x, double* y, int32_t kernel, double* dots) {
+  if (!h) return fail(h, TOPOPT_ERR_INVALID, "topopt_apply_ex: NULL handle");
+  TRY(use_device(h));
+  const bool hex8 = h->dim == 3 && h->nc == 3 && h->modal_ok;
+  if (kernel < 0 || kernel > 4) return fail(h, TOPOPT_ERR_INVALID, "topopt_apply_ex: unknown kernel");
+  if (kernel >= 2 && !hex8) return fail(h, TOPOPT_ERR_INVALID, "topopt_apply_ex: hex8 modal kernels need a brick/isotropic hex8 Ke");
+  if (x) TRY(upload_dofs(h, x, h->d_p));
+  TRY(exchange_halo(h, h->d_p));
+  CGState zero;
+  std::memset(&zero, 0, sizeof(zero));
+  zero.world = 1;  // the reduction stays rank-local; summed below
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_st, &zero, sizeof(CGState), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+  switch (kernel) {
+    case 0: TRY(launch_apply<true>(h, h->d_p, h->d_Ap, FIN_NONE)); break;
+    case 1: {  // dense node-centric gather
+      const int grid = grid_for((long long)h->g.S * h->g.nown, kReduceBlocks);
+#define CALL(D, C) LAUNCH(h, (k_apply<D, C, true>), grid, h->g, h->d_p, h->d_Ap, h->d_E, h->d_fixed, h->fixed_diag, h->d_partials, h->d_st, FIN_NONE)
+      DISPATCH(h, CALL);
+#undef CALL
+      TRY(check_launch(h, "k_apply"));
+      break;
+    }
+    case 2: TRY((launch_hex8_modal<16, true, false, false, true>(h, h->d_p, h->d_Ap, FIN_NONE, nullptr, nullptr))); break;
+    case 3: TRY((launch_hex8_modal2<12, true, false>(h, h->d_p, h->d_Ap, FIN_NONE))); break;
+    case 4: TRY((launch_hex8_ring<2, false>(h, h->d_p, h->d_Ap, FIN_NONE))); break;
+  }
+  CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+  if (h->world > 1)
+    NCCL_TRY(h, g_nccl.AllReduce(h->d_st->sums, h->d_st->sums, 2, ncclDouble, ncclSum, h->comm, h->stream));
+  if (y) TRY(download_dofs(h, h->d_Ap, y));
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_st, h->d_st, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  TRY(sync(h));
+  if (dots) {
+    dots[0] = h->h_st->sums[0];
+    dots[1] = kernel == 4 ? h->h_st->sums[1] : 0.0;
+  }
   float ms = 0;
   CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->stats.last_apply_ms = ms;
@@ -1515,16 +1681,52 @@ int topopt_time_kernel(topopt_handle* h, topopt_filter* f, int32_t which, int32_
   float ms = 0;
   switch (which) {
     case 0:
-      CUDA_TRY(h, cudaMemcpyAsync(h->d_p, h->d_b, sizeof(double) * h->nloc_dofs, cudaMemcpyDeviceToDevice, h->stream));
+    case 7:
+    case 8: {
+      // The K.u launch of the CG loop, as the loop issues it: dense direction vector (zero on prescribed
+      // dofs), fused dot product(s), no scalar step.  0 = the kernel the default CG selects, 7 = previous
+      // generation (two-row / one-row shuffle kernels), 8 = ring-staged kernel with both dot products.
+      CGState zero;
+      std::memset(&zero, 0, sizeof(zero));
+      zero.world = 1;
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_st, &zero, sizeof(CGState), cudaMemcpyHostToDevice, h->stream));
+      LAUNCH(h, k_fill_dense, kReduceBlocks, h->off, h->nown_dofs, h->d_p);
+#define CALL(D, C) LAUNCH(h, (k_apply_zero<C>), grid_for(h->nloc_nodes, kWideGrid), (long long)h->nloc_nodes, h->d_fixed, h->d_p)
+      DISPATCH(h, CALL);
+#undef CALL
+      TRY(exchange_halo(h, h->d_p));
+      const bool hex8 = h->dim == 3 && h->nc == 3 && h->modal_ok;
+      const int saved_ring = h->kxu_ring;
+      if (which == 7) h->kxu_ring = 0;
+      auto once = [&]() -> int {
+        if (which == 8 && !(hex8 && use_ring(h))) return fail(h, TOPOPT_ERR_INVALID, "topopt_time_kernel: ring kernel not applicable");
+        if (hex8 && use_ring(h)) return which == 8 ? launch_hex8_ring<2, false>(h, h->d_p, h->d_Ap, FIN_NONE) : launch_hex8_ring<1, false>(h, h->d_p, h->d_Ap, FIN_NONE);
+        return launch_apply<true>(h, h->d_p, h->d_Ap, FIN_NONE);
+      };
+      int rc = once();  // warm-up (attribute setup, instruction cache)
       CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
-      for (int r = 0; r < reps; ++r) TRY(launch_apply<false>(h, h->d_p, h->d_Ap, FIN_NONE));
+      for (int r = 0; r < reps && rc == TOPOPT_OK; ++r) rc = once();
       CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+      h->kxu_ring = saved_ring;
+      TRY(rc);
       break;
+    }
     case 1:
-    case 6: {
+    case 6:
+    case 9: {
+      // `reps` CG iterations on a dense right-hand side (every vector is live from the first iteration)
       o.op = which == 6 ? TOPOPT_OP_ASSEMBLED : TOPOPT_OP_MATRIX_FREE;
+      o.variant = which == 9 ? TOPOPT_CG_SINGLE_PASS : TOPOPT_CG_REFERENCE;
+      LAUNCH(h, k_fill_dense, kReduceBlocks, h->off, h->nown_dofs, h->d_rhs);
+#define CALL(D, C) LAUNCH(h, (k_apply_zero<C>), grid_for(h->nloc_nodes, kWideGrid), (long long)h->nloc_nodes, h->d_fixed, h->d_rhs)
+      DISPATCH(h, CALL);
+#undef CALL
+      const int saved_variant = h->cg_variant_env;
+      h->cg_variant_env = -1;
       topopt_cg_result r{};
-      TRY(cg_solve(h, h->d_b, &o, &r, true, reps));
+      const int rc = cg_solve(h, h->d_rhs, &o, &r, true, reps);
+      h->cg_variant_env = saved_variant;
+      TRY(rc);
       *ms_out = r.solve_ms / std::max(1, r.iters);
       return TOPOPT_OK;
     }

@@ -49,6 +49,7 @@ struct CGState {
   double gsums[8];  // after the allreduce (aliases sums when world == 1)
   double res, prev_res, rho, rho_prev, alpha, beta, tol, abstol, reltol, energy, pAp;
   int iters, done, converged, maxiter, criteria, precond, nonfinite, world;
+  int variant;      // 0 = IterativeSolvers recurrence, 1 = single-pass recurrence (FIN_PAP2 / FIN_RR2)
   unsigned int counter;
   PeerComm* peer;   // non-null: reductions are all-reduced inside the kernel over peer memory
 };
@@ -82,7 +83,7 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
   return v;
 }
 
-enum { FIN_NONE = 0, FIN_INIT = 1, FIN_PAP = 2, FIN_RR = 3, FIN_PLAIN = 4 };
+enum { FIN_NONE = 0, FIN_INIT = 1, FIN_PAP = 2, FIN_RR = 3, FIN_PLAIN = 4, FIN_PAP2 = 5, FIN_RR2 = 6 };
 
 // scalar recurrences of IterativeSolvers.cg! (CGIterable / PCGIterable iterate) and the
 // convergence tests of src/FEA/convergence_criteria.jl:26-45, evaluated on the device so the
@@ -94,6 +95,20 @@ __device__ inline void cg_finalize(CGState* st, int which) {
     st->alpha = st->precond ? st->rho / s[0] : (st->res * st->res) / s[0];
     return;
   }
+  if (which == FIN_PAP2) {
+    // Single-pass variant: s = {p.Ap, Ap.Ap}.  With r.Ap = p.Ap (A-orthogonality of the directions)
+    // |r - alpha Ap|^2 = alpha^2 Ap.Ap - r.r, so beta is known BEFORE the residual is updated and
+    // x += alpha p, r -= alpha Ap, p = r + beta p become one pass over the vectors.  st->rho is the TRUE
+    // r.r accumulated by that pass (FIN_RR2), so the prediction error does not accumulate.
+    st->pAp = s[0];
+    const double rho = st->rho;
+    const double alpha = rho / s[0];
+    double rho_next = fma(alpha * alpha, s[1], -rho);
+    if (!(rho_next > 0.0)) rho_next = 0.0;  // cancellation at a (near-)exact solve: restart with steepest descent
+    st->alpha = alpha;
+    st->beta = rho_next / rho;
+    return;
+  }
   if (which == FIN_INIT) {
     st->res = sqrt(s[0]);
     st->tol = fmax(st->reltol * st->res, st->abstol);
@@ -101,12 +116,14 @@ __device__ inline void cg_finalize(CGState* st, int which) {
     st->rho_prev = 1.0;
     st->energy = 0.0;
     st->iters = 0;
-  } else {  // FIN_RR
+  } else {  // FIN_RR, FIN_RR2
     st->prev_res = st->res;
     st->res = sqrt(s[0]);
     st->iters += 1;
   }
-  if (st->precond) {
+  if (st->variant == 1) {
+    st->rho = s[0];
+  } else if (st->precond) {
     if (which == FIN_RR) st->rho_prev = st->rho;
     st->rho = s[1];
     st->beta = st->rho / st->rho_prev;
@@ -129,11 +146,22 @@ __device__ inline void cg_finalize(CGState* st, int which) {
   st->done = (conv || st->iters >= st->maxiter || st->nonfinite) ? 1 : 0;
 }
 
+// "this rank's direction vector is final for this iteration": told to both slab neighbours, which read
+// its boundary planes over NVLink inside their K.u kernel
+__device__ __forceinline__ void signal_halo_flags(CGState* st) {
+  PeerComm* pc = st->peer;
+  const unsigned long long seq = pc->halo_seq + 1;
+  __threadfence_system();
+  if (pc->rank + 1 < pc->world) *(volatile unsigned long long*)&pc->block[pc->rank + 1]->halo_flag[0] = seq;
+  if (pc->rank > 0) *(volatile unsigned long long*)&pc->block[pc->rank - 1]->halo_flag[1] = seq;
+  pc->halo_seq = seq;
+}
+
 // Each block deposits NS partial sums; the last block to arrive adds all partials in a fixed
 // order, publishes them and (single-GPU) runs the scalar step.
 template <int NS>
 __device__ __forceinline__ void block_partials_finish(const double (&v)[NS], double* partials,
-                                                      CGState* st, int which, double* sm) {
+                                                      CGState* st, int which, double* sm, bool signal_halo = false) {
   __shared__ bool is_last;
   double r[NS];
 #pragma unroll
@@ -148,6 +176,8 @@ __device__ __forceinline__ void block_partials_finish(const double (&v)[NS], dou
   __syncthreads();
   if (!is_last) return;
   __threadfence();
+  // every block's stores are visible now: the vector this kernel wrote may be read by the neighbours
+  if (signal_halo && threadIdx.x == 0) signal_halo_flags(st);
   double a[NS];
 #pragma unroll
   for (int k = 0; k < NS; ++k) a[k] = 0.0;
@@ -450,12 +480,30 @@ __global__ void k_diag(Geo g, double* __restrict__ d, const double* __restrict__
   }
 }
 
+// deterministic dense pseudo-random values in (-1, 1) on owned dofs (kernel timing on a live-like vector)
+__global__ void __launch_bounds__(kBlock) k_fill_dense(long long off, long long n, double* __restrict__ v) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    unsigned long long z = (unsigned long long)t * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    v[off + t] = (double)(long long)(z >> 11) * (1.0 / 4503599627370496.0) - 1.0;
+  }
+}
+
+// out = a u + b v on owned dofs
+__global__ void __launch_bounds__(kBlock) k_axpby(long long off, long long n, double a, const double* __restrict__ u, double b,
+                                                  const double* __restrict__ v, double* __restrict__ out) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+    out[off + t] = fma(a, u[off + t], b * v[off + t]);
+}
+
 // ---- CG vector kernels (IterativeSolvers cg!, see cg_finalize) --------------------------------
 // r = b, x = 0, p = 0 on owned dofs; sums: r.r [, r.(r/D)]
 __global__ void __launch_bounds__(kBlock) k_cg_init(long long off, long long n, const double* __restrict__ b,
                                                     double* __restrict__ x, double* __restrict__ r,
                                                     double* __restrict__ p, const double* __restrict__ D,
-                                                    double* partials, CGState* st) {
+                                                    double* partials, CGState* st, int p_is_r, int signal_halo) {
   __shared__ double sm[32];
   double v[2] = {0.0, 0.0};
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
@@ -463,12 +511,12 @@ __global__ void __launch_bounds__(kBlock) k_cg_init(long long off, long long n, 
     const long long k = off + t;
     const double bv = b[k];
     r[k] = bv;
-    x[k] = 0.0;
-    p[k] = 0.0;
+    if (x) x[k] = 0.0;  // x == nullptr: warm start, b already holds b - K x0
+    p[k] = p_is_r ? bv : 0.0;  // single-pass variant: the first direction is formed here
     v[0] = fma(bv, bv, v[0]);
     if (D) v[1] = fma(bv, bv / D[k], v[1]);
   }
-  block_partials_finish<2>(v, partials, st, FIN_INIT, sm);
+  block_partials_finish<2>(v, partials, st, FIN_INIT, sm, signal_halo != 0);
 }
 
 // p = z + beta p   (z = r, or r/D when preconditioned).  4 independent elements per thread and
@@ -508,14 +556,7 @@ __global__ void __launch_bounds__(kBlock) k_update_p(long long off, long long n,
     __syncthreads();
     if (threadIdx.x == 0) {
       const unsigned int tk = atomicInc(&st->counter, gridDim.x - 1);
-      if (tk == gridDim.x - 1) {
-        PeerComm* pc = st->peer;
-        const unsigned long long seq = pc->halo_seq + 1;
-        __threadfence_system();
-        if (pc->rank + 1 < pc->world) *(volatile unsigned long long*)&pc->block[pc->rank + 1]->halo_flag[0] = seq;
-        if (pc->rank > 0) *(volatile unsigned long long*)&pc->block[pc->rank - 1]->halo_flag[1] = seq;
-        pc->halo_seq = seq;
-      }
+      if (tk == gridDim.x - 1) signal_halo_flags(st);
     }
   }
 }
@@ -565,6 +606,45 @@ __global__ void __launch_bounds__(kBlock) k_update_xr(long long off, long long n
   }
   for (; t < n; t += stride) body(t, x[t], r[t], p[t], Ap[t]);
   block_partials_finish<4>(v, partials, st, FIN_RR, sm);
+}
+
+// Single-pass variant (cg_finalize FIN_PAP2 / FIN_RR2): x += alpha p ; r -= alpha Ap ; p = r + beta p ;
+// sums: r.r of the NEW residual.  56 bytes per dof instead of 72 for the two separate passes.
+__global__ void __launch_bounds__(kBlock) k_update_xrp(long long off, long long n, double* __restrict__ x,
+                                                       double* __restrict__ r, double* __restrict__ p,
+                                                       const double* __restrict__ Ap, double* partials, CGState* st,
+                                                       int signal_halo) {
+  __shared__ double sm[32];
+  if (st->done) return;
+  const double alpha = st->alpha, beta = st->beta;
+  double v[1] = {0.0};
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  x += off;
+  r += off;
+  p += off;
+  Ap += off;
+  auto body = [&](long long k, double xk, double rk, double pk, double apk) {
+    const double rv = fma(-alpha, apk, rk);
+    x[k] = fma(alpha, pk, xk);
+    r[k] = rv;
+    p[k] = fma(beta, pk, rv);
+    v[0] = fma(rv, rv, v[0]);
+  };
+  for (; t + 3 * stride < n; t += 4 * stride) {
+    double xk[4], rk[4], pk[4], ak[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      xk[k] = x[t + k * stride];
+      rk[k] = r[t + k * stride];
+      pk[k] = p[t + k * stride];
+      ak[k] = Ap[t + k * stride];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) body(t + k * stride, xk[k], rk[k], pk[k], ak[k]);
+  }
+  for (; t < n; t += stride) body(t, x[t], r[t], p[t], Ap[t]);
+  block_partials_finish<1>(v, partials, st, FIN_RR2, sm, signal_halo != 0);
 }
 
 // plain dot over owned dofs -> st->sums[0]

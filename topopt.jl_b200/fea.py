@@ -104,7 +104,8 @@ class GenericFEASolver:
     functions and filters read: problem, u, lhs, rhs, vars, penalty, xmin, cg_max_iter, abstol,
     preconditioner, conv.  The device handle replaces globalinfo/elementinfo."""
 
-    def __init__(self, solver_type, problem, xmin, penalty, abstol, cg_max_iter, preconditioner, conv, reltol, device, comm, check_every):
+    def __init__(self, solver_type, problem, xmin, penalty, abstol, cg_max_iter, preconditioner, conv, reltol, device, comm, check_every,
+                 cg_variant=0, warm_start=False, refresh_preconditioner=False):
         self.solver_type = solver_type
         self.problem = problem
         self.xmin = float(xmin)
@@ -117,6 +118,11 @@ class GenericFEASolver:
         self.preconditioner_initialized = False
         self.conv = conv
         self.check_every = int(check_every)
+        # extensions over the reference (all off by default): see include/topopt_cuda.h topopt_cg_opts
+        self.cg_variant = int(cg_variant)
+        self.warm_start = bool(warm_start)
+        self.refresh_preconditioner = bool(refresh_preconditioner)
+        self._solved_once = False
         self.u = np.zeros(problem.ndof)
         self.lhs = np.zeros(problem.ndof)
         self.rhs = np.zeros(problem.ndof)
@@ -182,6 +188,9 @@ class GenericFEASolver:
         o.precond = _lib.PRECOND_NONE if self.preconditioner in (None, "identity") else _lib.PRECOND_JACOBI
         o.criteria = self.conv.code
         o.check_every = over.get("check_every", self.check_every)
+        o.variant = over.get("variant", self.cg_variant)
+        o.warm_start = 1 if over.get("warm_start", self.warm_start and self._solved_once) else 0
+        o.refresh_precond = 1 if over.get("refresh_precond", self.refresh_preconditioner) else 0
         return o
 
     def set_density(self, x=None):
@@ -207,7 +216,8 @@ class GenericFEASolver:
             # UpdatePreconditioner! runs once per solver lifetime (solvers_api.jl:187-192)
             self._check(self._lib.topopt_set_jacobi(self._handle, None))
             self.preconditioner_initialized = True
-        opts = self.cg_opts()
+        default_rhs = assemble_f and rhs is None
+        opts = self.cg_opts() if default_rhs else self.cg_opts(warm_start=False)  # a warm start only makes sense for the same load
         res = _lib.CGResult()
         if rhs is not None and np.ndim(rhs) == 2:
             rhs = np.asarray(rhs, dtype=np.float64)
@@ -224,6 +234,7 @@ class GenericFEASolver:
             self._check(
                 self._lib.topopt_solve(self._handle, None, _lib.ptr(target) if download else None, C.byref(opts), C.byref(res))
             )
+            self._solved_once = True
         else:
             b = np.ascontiguousarray(self.rhs if rhs is None else rhs, dtype=np.float64)
             target = self.lhs if lhs is None else lhs
@@ -237,6 +248,13 @@ class GenericFEASolver:
         y = np.empty(self.problem.ndof)
         self._check(self._lib.topopt_apply(self._handle, _lib.ptr(np.ascontiguousarray(x, dtype=np.float64)), _lib.ptr(y)))
         return y
+
+    def mul_ex(self, x, kernel):
+        """topopt_apply_ex: K x through one specific kernel generation; returns (y, x.y, y.y)."""
+        y = np.empty(self.problem.ndof)
+        dots = (C.c_double * 2)()
+        self._check(self._lib.topopt_apply_ex(self._handle, _lib.ptr(np.ascontiguousarray(x, dtype=np.float64)), _lib.ptr(y), kernel, dots))
+        return y, dots[0], dots[1]
 
     def assemble(self):
         """assemble! + apply! (assemble.jl:28-90): returns (nzval in CSC order, f)."""
@@ -273,7 +291,8 @@ def getcompliance(solver):
 
 
 def FEASolver(Solver, problem, *, xmin=1e-3, penalty=None, abstol=1e-7, cg_max_iter=700, preconditioner=None,
-              conv=None, reltol=None, device=0, comm=None, check_every=0):
+              conv=None, reltol=None, device=0, comm=None, check_every=0, cg_variant=0, warm_start=False,
+              refresh_preconditioner=False):
     """FEASolver(Solver, problem; xmin, penalty, abstol, cg_max_iter, preconditioner, conv)
     with the reference's defaults (solvers_api.jl:468-489).  ``reltol`` is IterativeSolvers'
     sqrt(eps) unless overridden (the reference cannot override it)."""
@@ -294,4 +313,7 @@ def FEASolver(Solver, problem, *, xmin=1e-3, penalty=None, abstol=1e-7, cg_max_i
         device,
         comm,
         check_every,
+        cg_variant,
+        warm_start,
+        refresh_preconditioner,
     )

@@ -26,6 +26,7 @@ def simp_eval(solver, filt, x, grad_out=None):
             solver.xmin, C.byref(opts), C.byref(obj), _lib.ptr(grad_out), C.byref(res),
         )
     )
+    solver._solved_once = True
     return obj.value, res
 
 
