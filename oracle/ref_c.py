@@ -115,3 +115,21 @@ class RefProblem:
         y = np.empty_like(x)
         self.lib.ref_filter(self.h, _dp(self.sizes), rmin, _dp(x), _dp(y))
         return y
+
+
+def point_load_cantilever_inputs(nels, sizes=None, E=1.0, nu=0.3, force=1.0):
+    """Inputs of the C port for PointLoadCantilever built from the ORACLE only (no product code):
+    (Ke, prescribed dofs 1-based sorted, fixedload).  Same construction as
+    topopt_oracle.PointLoadCantilever (problem_types.jl:162-223) without the ragged Metadata tables,
+    so it stays cheap at 12.8 M dofs."""
+    import topopt_oracle as o
+
+    g = o.Grid(nels, sizes)
+    block = o.ferrite_node_blocks(g.cells, g.nnodes)
+    ncomp = g.dim
+    fixed_nodes = np.nonzero(g.left())[0]
+    prescribed = np.unique((ncomp * block[fixed_nodes][:, None] + np.arange(ncomp)[None, :]).ravel()) + 1
+    fnode = np.nonzero(g.right() & g.middley())[0][0]
+    f = np.zeros(ncomp * g.nnodes)
+    f[ncomp * block[fnode] + 1] = -force
+    return o.element_stiffness(g.dim, g.sizes, E, nu), prescribed.astype(np.int64), f

@@ -1,0 +1,26 @@
+"""K.u ring-kernel sweep over env settings: each argv[2:] is "K=V,K=V"."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+
+import topopt_jl_b200 as t
+
+nels = tuple(int(v) for v in sys.argv[1].split(","))
+prob = t.PointLoadCantilever(nels)
+rho = np.random.default_rng(0).uniform(0.2, 1.0, prob.nel)
+bytes_kxu = 16 * prob.ndof + 8 * prob.nel
+for cfg in sys.argv[2:]:
+    kv = dict(p.split("=") for p in cfg.split(",") if p)
+    for k, v in kv.items():
+        os.environ[k] = v
+    s = t.FEASolver(t.CUDAMatrixFreeSolver, prob, penalty=t.PowerPenaltyFun(3.0), xmin=1e-6)
+    s.set_density(rho)
+    s.time_kernel(8, 3)
+    ms = min(s.time_kernel(8, 30) for _ in range(3))
+    print(f"{cfg:50s} {ms * 1e3:9.2f} us {bytes_kxu / ms / 1e6:8.1f} GB/s alg", flush=True)
+    s.close()
+    for k in kv:
+        os.environ.pop(k, None)

@@ -81,6 +81,7 @@ struct topopt_handle {
   bool modal_ok = false;  // Ke has the brick/isotropic modal sparsity pattern
   int kxu_ty = 16, kxu_waves = 1, kxu_nsync = 1, kxu_2row = 1;  // 2row: 0 = one-row kernel, 1 = auto, else thread rows
   int kxu_ring = 1;       // ring-staged kernel for premasked inputs (CG directions): 0 = off, 1 = auto, else thread rows
+  int kxu_stagger = 0;    // ring kernel: stagger the thread rows at segment starts
   int kxu_ring_min = 24;  // fewest owned node planes per rank for which the ring kernel is selected
   int cg_variant_env = -1;  // TOPOPT_CG_VARIANT overrides topopt_cg_opts.variant (diagnostics)
   double fixed_diag = 0.0, cellvol = 1.0;
@@ -198,10 +199,12 @@ int check_launch(topopt_handle* h, const char* what) {
   return TOPOPT_OK;
 }
 
+// + 64 bytes: the ring-staged kernel's 16-byte aligned bulk copies may read up to 15 bytes past a row end
 template <typename T>
 int dev_alloc(topopt_handle* h, T** p, size_t n) {
-  CUDA_TRY(h, cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
-  CUDA_TRY(h, cudaMemsetAsync(*p, 0, std::max<size_t>(n, 1) * sizeof(T), h->stream));
+  const size_t bytes = std::max<size_t>(n, 1) * sizeof(T) + 64;
+  CUDA_TRY(h, cudaMalloc((void**)p, bytes));
+  CUDA_TRY(h, cudaMemsetAsync(*p, 0, bytes, h->stream));
   return TOPOPT_OK;
 }
 
@@ -378,36 +381,43 @@ int launch_hex8_ring_t(topopt_handle* h, const double* x, double* y, int fin) {
   const Geo& g = h->g;
   constexpr int OWNR = 2 * TYT - 1;
   const int tilesX = (g.NX + 30) / 31, tilesY = (g.NY + OWNR - 1) / OWNR;
-  int grid = 148 * std::max(1, h->kxu_waves);
+  int grid = 148 * (TYT <= 5 ? 2 : 1) * std::max(1, h->kxu_waves);
   const long long units = (long long)tilesX * tilesY * g.nown;
   if (grid > units) grid = (int)units;
-  const size_t smem = (size_t)NST * (2 * TYT + 1) * kRingPitch + sizeof(double) * 2 * 6 * TYT * 32;
-  static std::atomic<unsigned long long> attr_mask{0};
-  TRY(ensure_dyn_smem(h, k_apply_hex8_ring<TYT, NST, DOT, PEER>, smem, attr_mask));
+  const size_t smem = hex8_ring_smem(TYT, NST);  // per-warp rings + y exchange
   const double* xlo = nullptr;
   const double* xhi = nullptr;
   if (PEER) {
     if (h->peer_p_lo) xlo = h->peer_p_lo + (size_t)h->plane_dofs * h->nown_lower;
     if (h->peer_p_hi) xhi = h->peer_p_hi + (size_t)h->plane_dofs;
   }
-  k_apply_hex8_ring<TYT, NST, DOT, PEER><<<grid, 32 * TYT, smem, h->stream>>>(g, x, y, h->d_E, h->d_fixed, h->fixed_diag, tilesX, tilesY,
-                                                                             h->d_partials, h->d_st, fin, xlo, xhi);
+  if (h->kxu_stagger) {
+    static std::atomic<unsigned long long> attr_mask{0};
+    TRY(ensure_dyn_smem(h, k_apply_hex8_ring<TYT, NST, DOT, PEER, true>, smem, attr_mask));
+    k_apply_hex8_ring<TYT, NST, DOT, PEER, true><<<grid, 32 * (TYT + 1), smem, h->stream>>>(g, x, y, h->d_E, h->d_fixed, h->fixed_diag, tilesX, tilesY,
+                                                                                           h->d_partials, h->d_st, fin, xlo, xhi);
+  } else {
+    static std::atomic<unsigned long long> attr_mask{0};
+    TRY(ensure_dyn_smem(h, k_apply_hex8_ring<TYT, NST, DOT, PEER, false>, smem, attr_mask));
+    k_apply_hex8_ring<TYT, NST, DOT, PEER, false><<<grid, 32 * (TYT + 1), smem, h->stream>>>(g, x, y, h->d_E, h->d_fixed, h->fixed_diag, tilesX, tilesY,
+                                                                                            h->d_partials, h->d_st, fin, xlo, xhi);
+  }
   h->stats.kernel_launches += 1;
   return check_launch(h, "k_apply_hex8_ring");
 }
 
-// thread rows per CTA of the ring kernel: fewest wasted node rows for this grid (a tile owns 2*TYT-1 rows)
+// compute warps (thread rows) per CTA of the ring kernel: fewest node rows processed for this grid (a tile of
+// 2*TYT rows owns 2*TYT-1).  With the producer warp, 11 compute warps is the most that fits 156 registers.
 inline int ring_rows(const topopt_handle* h) {
   if (h->kxu_ring > 1) return h->kxu_ring;
-  double best = -1.0;
-  int tyt = 12;
-  const int cand[3] = {12, 10, 8};
+  long long best = -1;
+  int tyt = 10;
+  const int cand[3] = {11, 10, 8};
   for (int k = 0; k < 3; ++k) {
     const int own = 2 * cand[k] - 1;
-    const int tiles = (h->g.NY + own - 1) / own;
-    const double eff = (double)h->g.NY / ((double)tiles * 2 * cand[k]);
-    if (eff > best + 1e-9) {
-      best = eff;
+    const long long rows = (long long)((h->g.NY + own - 1) / own) * 2 * cand[k];
+    if (best < 0 || rows < best) {
+      best = rows;
       tyt = cand[k];
     }
   }
@@ -421,9 +431,10 @@ inline bool use_ring(const topopt_handle* h) {
 template <int DOT, bool PEER>
 int launch_hex8_ring(topopt_handle* h, const double* x, double* y, int fin) {
   switch (ring_rows(h)) {
+    case 5: return launch_hex8_ring_t<5, DOT, PEER>(h, x, y, fin);
     case 8: return launch_hex8_ring_t<8, DOT, PEER>(h, x, y, fin);
-    case 10: return launch_hex8_ring_t<10, DOT, PEER>(h, x, y, fin);
-    default: return launch_hex8_ring_t<12, DOT, PEER>(h, x, y, fin);
+    case 11: return launch_hex8_ring_t<11, DOT, PEER>(h, x, y, fin);
+    default: return launch_hex8_ring_t<10, DOT, PEER>(h, x, y, fin);
   }
 }
 
@@ -1013,6 +1024,7 @@ int topopt_create(const topopt_desc* d, topopt_handle** out) {
     if (const char* e = getenv("TOPOPT_KXU_2ROW")) h->kxu_2row = atoi(e);
     if (const char* e = getenv("TOPOPT_KXU_RING")) h->kxu_ring = atoi(e);
     if (const char* e = getenv("TOPOPT_KXU_RING_MIN")) h->kxu_ring_min = atoi(e);
+    if (const char* e = getenv("TOPOPT_KXU_STAGGER")) h->kxu_stagger = atoi(e);
   }
   if (const char* e = getenv("TOPOPT_CG_VARIANT")) h->cg_variant_env = atoi(e);
 
@@ -1101,7 +1113,7 @@ int topopt_create(const topopt_desc* d, topopt_handle** out) {
   CTRY(dev_alloc(h, &h->d_block, h->nloc_nodes));
   CTRY(dev_alloc(h, &h->d_fixed, h->nloc_nodes));
   for (double** v : {&h->d_b, &h->d_fload, &h->d_u, &h->d_r, &h->d_p, &h->d_p2, &h->d_Ap, &h->d_D, &h->d_rhs, &h->d_lam, &h->d_tmp})
-    CTRY(dev_alloc(h, v, h->nloc_dofs + 4));  // + 32 bytes: 16-byte aligned bulk copies may over-read a row end
+    CTRY(dev_alloc(h, v, h->nloc_dofs));
   for (double** v : {&h->d_E, &h->d_dE, &h->d_rho, &h->d_cell, &h->d_grad}) CTRY(dev_alloc(h, v, h->nloc_el));
   CTRY(dev_alloc(h, &h->d_full_dof, h->ndof));
   for (double** v : {&h->d_full_el, &h->d_design, &h->d_xf, &h->d_gfull}) CTRY(dev_alloc(h, v, h->nel));

@@ -116,297 +116,417 @@ __device__ __forceinline__ void hex8_core(const RowX& L, const RowX& U, double (
   }
 }
 
+// One stage of a warp's private ring: node rows A, B, C of a plane (E_e and the prescribed-dof flags, 10 bytes per
+// thread and step, come through ordinary loads issued one step ahead).
+constexpr int kRingStage = 3 * kRingPitch;
+constexpr int kRingJobs = 3;  // bulk copies per compute warp and plane
+
+__host__ __device__ constexpr size_t hex8_ring_smem(int tyt, int nst) {
+  return (size_t)tyt * nst * kRingStage + sizeof(double) * 3 * 6 * (tyt + 1) * 32;
+}
+
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Warp-specialised: TYT compute warps (thread rows) + ONE producer warp that issues every bulk copy of the
+// CTA (the TMA producer / consumer pipeline: full[w][s] = data landed, empty[w][s] = stage released).
 // DOT: 0 = none, 1 = sum x.y, 2 = sum x.y and sum y.y (single-pass CG)
-template <int TYT, int NST, int DOT, bool PEER>
-__global__ void __launch_bounds__(32 * TYT, 1)
+template <int TYT, int NST, int DOT, bool PEER, bool STAGGER>
+__global__ void __launch_bounds__(32 * (TYT + 1), (TYT <= 5 ? 2 : 1))
     k_apply_hex8_ring(Geo g, const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ E,
                       const unsigned char* __restrict__ fixed, double fixed_diag, int tilesX, int tilesY, double* partials,
                       CGState* st, int fin, const double* __restrict__ xlo, const double* __restrict__ xhi) {
-  constexpr int RR = 2 * TYT + 1;        // ring rows per plane (rows A, B of every thread row + row C of the last)
-  constexpr int STAGE = RR * kRingPitch; // bytes per plane
-  constexpr int OWNR = 2 * TYT - 1;      // node rows a tile owns
+  constexpr int WRING = NST * kRingStage;  // bytes of one warp's private ring
+  constexpr int OWNR = 2 * TYT - 1;        // node rows a tile owns
   constexpr int NS = DOT == 2 ? 2 : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  unsigned char* ring = smem_raw;
-  double(*yb)[6][TYT][32] = reinterpret_cast<double(*)[6][TYT][32]>(smem_raw + NST * STAGE);  // [2] parity buffers
-  __shared__ uint64_t full[NST];
-  __shared__ int sflag[TYT];
+  // y exchange: [step % 3][value][thread row + 1][lane]; row 0 stays zero (the bottom thread row has no lower neighbour)
+  double(*yb)[6][TYT + 1][32] = reinterpret_cast<double(*)[6][TYT + 1][32]>(smem_raw + TYT * WRING);
+  __shared__ uint64_t full[TYT][NST], empty[TYT][NST];
+  __shared__ int sflag[TYT], sstart[TYT];
   __shared__ double sm[32];
   if (DOT && st->done) return;
   const int tid = threadIdx.x;
-  const int tx = tid & 31, ty = tid >> 5;
+  const int tx = tid & 31, wid = tid >> 5;
+  const bool producer = wid == TYT;
+  // the warp scheduler favours high warp ids: the bottom thread row, which every other row depends on
+  // through the y reduction chain, gets the highest compute warp id (the producer sits above it)
+  const int ty = producer ? 0 : TYT - 1 - wid;
   const unsigned FULL = 0xffffffffu;
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < NST; ++s) mbar_init(&full[s], TYT);
+  if (tid < TYT * NST) {
+    mbar_init(&full[tid / NST][tid % NST], kRingJobs);
+    mbar_init(&empty[tid / NST][tid % NST], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < TYT) sflag[tid] = 0;
-  // stale ring contents are read for out-of-domain nodes (their elements carry E = 0): keep them finite
-  for (int i = tid; i < NST * STAGE / 16; i += 32 * TYT) reinterpret_cast<uint4*>(ring)[i] = make_uint4(0, 0, 0, 0);
+  if (tid < TYT) sflag[tid] = sstart[tid] = 0;
+  // stale ring contents are read for out-of-domain nodes (their elements get E = 0): keep them finite
+  for (int i = tid; i < TYT * WRING / 16; i += 32 * (TYT + 1)) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 3 * 6 * (TYT + 1) * 32; i += 32 * (TYT + 1)) (&yb[0][0][0][0])[i] = 0.0;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
 
-  int it = 0;             // published-step counter (monotonic across segments)
-  unsigned fbase = 0;     // fills issued before this segment: fill f -> stage f % NST, parity (f / NST) & 1
   double dots[NS];
 #pragma unroll
   for (int k = 0; k < NS; ++k) dots[k] = 0.0;
-
   const long long units = (long long)tilesX * tilesY * g.nown;
   long long u0 = units * blockIdx.x / gridDim.x;
   const long long u1 = units * (blockIdx.x + 1) / gridDim.x;
-  while (u0 < u1) {
-    const int tile = (int)(u0 / g.nown);
-    const int zoff = (int)(u0 % g.nown);
-    const int zlen = (int)min((long long)(g.nown - zoff), u1 - u0);
-    u0 += zlen;
-    const int bx = tile % tilesX, by = tile / tilesX;
-    const int c0 = bx * 31 - 1, r0 = by * OWNR - 1;  // node column of lane 0 / node row of ring row 0
-    const int z0 = 1 + zoff, z1 = z0 + zlen;         // owned local planes [z0, z1); planes z0-1 .. z1 are read
-    const int first = z0 - 1, last = z1;
-    const int c_lo = max(c0, 0), c_hi = min(c0 + 33, g.NX), cnt = c_hi - c_lo;
-    const int shift = c_lo - c0;              // 1 on the left-edge tile (column -1 does not exist)
-    const int dst_off = shift ? 32 : 0;       // keeps lane 0's (unused) slot inside the row buffer
-    __syncthreads();                          // the previous segment's ring / yb reads are complete
 
-    const int col = c0 + tx;
-    int rrow[3];          // node rows of A, B, C
-    unsigned rowpar[3];   // alignment parity of the row's first copied node
-    int base_off[3];      // byte offset of this lane's node in the ring row (before the alignment lead)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      rrow[k] = r0 + 2 * ty + k;
-      rowpar[k] = (unsigned)(((long long)rrow[k] * g.NX + c_lo) & 1) << 3;
-      base_off[k] = (2 * ty + k) * kRingPitch + dst_off - 24 * shift + 24 * tx;
-    }
-    bool node_ok[2], own[2], el_ok[2];
-    long long ncol[2], ecol[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      node_ok[k] = col >= 0 && col < g.NX && rrow[k] >= 0 && rrow[k] < g.NY;
-      el_ok[k] = col >= 0 && col < g.nx && rrow[k] >= 0 && rrow[k] < g.ny;
-      ncol[k] = node_ok[k] ? (long long)rrow[k] * g.NX + col : 0;
-      ecol[k] = el_ok[k] ? (long long)rrow[k] * g.nx + col : 0;
-    }
-    own[0] = node_ok[0] && tx >= 1 && ty >= 1;  // row A of thread row 0 lacks the tile below
-    own[1] = node_ok[1] && tx >= 1;             // lane 0 lacks the element column to its left
-
-    if (PEER && (xlo != nullptr || xhi != nullptr)) {
-      const bool need_lo = xlo != nullptr && z0 == 1, need_hi = xhi != nullptr && z1 == g.nown + 1;
-      if ((need_lo || need_hi) && tid == 0) {
-        PeerComm* pc = st->peer;
-        const unsigned long long want = pc->halo_seq;
-        volatile unsigned long long* f = pc->block[pc->rank]->halo_flag;
-        long long spins = 0;
-        while ((need_lo && f[0] < want) || (need_hi && f[1] < want)) {
-          if (++spins > kSpinLimit) {
-            pc->timeout = 1;
-            break;
+  if (producer) {
+    // =========================== producer warp ===========================
+    unsigned fcount = 0;  // planes filled so far (every compute warp gets one fill per plane)
+    while (u0 < u1) {
+      const int tile = (int)(u0 / g.nown);
+      const int zoff = (int)(u0 % g.nown);
+      const int zlen = (int)min((long long)(g.nown - zoff), u1 - u0);
+      u0 += zlen;
+      const int bx = tile % tilesX, by = tile / tilesX;
+      const int c0 = bx * 31 - 1;
+      const int z0 = 1 + zoff, z1 = z0 + zlen, first = z0 - 1, last = z1;
+      const int c_lo = max(c0, 0), cnt = min(c0 + 33, g.NX) - c_lo;
+      const int shift = c_lo - c0;
+      if (PEER && (xlo != nullptr || xhi != nullptr)) {
+        // ghost planes are read from the slab neighbours' memory: wait for their "direction vector final" flag
+        const bool need_lo = xlo != nullptr && z0 == 1, need_hi = xhi != nullptr && z1 == g.nown + 1;
+        if ((need_lo || need_hi) && tx == 0) {
+          PeerComm* pc = st->peer;
+          const unsigned long long want = pc->halo_seq;
+          volatile unsigned long long* f = pc->block[pc->rank]->halo_flag;
+          long long spins = 0;
+          while ((need_lo && f[0] < want) || (need_hi && f[1] < want)) {
+            if (++spins > kSpinLimit) {
+              pc->timeout = 1;
+              break;
+            }
           }
+          __threadfence_system();
         }
-        __threadfence_system();
+        __syncwarp();
         asm volatile("fence.proxy.async;" ::: "memory");
       }
-      __syncthreads();
-    }
-    auto plane_ptr = [&](int P) -> const char* {
-      if (PEER) {
-        if (xlo != nullptr && P == 0) return reinterpret_cast<const char*>(xlo);
-        if (xhi != nullptr && P == g.nown + 1) return reinterpret_cast<const char*>(xhi);
-      }
-      return reinterpret_cast<const char*>(x + (long long)P * g.S * 3);
-    };
-    // lane 0 of every warp copies its rows A, B (and C for the last thread row) of plane P into stage f % NST
-    auto issue_fill = [&](int P, unsigned f) {
-      const int stg = (int)(f % NST);
-      const char* pp = plane_ptr(P);
-      unsigned char* sbase = ring + stg * STAGE;
-      const char* src[3];
-      uint32_t nb[3], total = 0;
+      // this lane's jobs: j = tx, tx + 32, ... -> (compute warp row w, node row k = A, B, C)
+      constexpr int NJ = kRingJobs * TYT, JPL = (NJ + 31) / 32;
+      long long jidx[JPL];
+      int jdst[JPL], jw[JPL];
+      bool jvalid[JPL], jok[JPL];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        nb[k] = 0;
-        src[k] = pp;
-        const bool want = (k < 2 || ty == TYT - 1) && rrow[k] >= 0 && rrow[k] < g.NY;
-        if (want) {
-          const char* a = pp + 24ll * ((long long)rrow[k] * g.NX + c_lo);
-          const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(a) & 15);
-          src[k] = a - lead;
-          nb[k] = (lead + 24u * (uint32_t)cnt + 15u) & ~15u;
-          total += nb[k];
+      for (int q = 0; q < JPL; ++q) {
+        const int j = tx + 32 * q;
+        const int w = j / kRingJobs, k = j % kRingJobs;
+        const int frow = by * OWNR - 1 + 2 * w + k;
+        jw[q] = w;
+        jvalid[q] = j < NJ;
+        jok[q] = j < NJ && frow >= 0 && frow < g.NY;
+        jidx[q] = 24ll * ((long long)frow * g.NX + c_lo);
+        jdst[q] = w * WRING + k * kRingPitch + (shift ? 32 : 0);
+      }
+      const uint32_t jbytes = 24u * (uint32_t)cnt;
+      for (int P = first; P <= last; ++P, ++fcount) {
+        const int s = (int)(fcount % NST);
+        const uint32_t rel_par = ((fcount / NST) + 1u) & 1u;  // parity of the release of the previous use of stage s
+        const char* pp = reinterpret_cast<const char*>(x + (long long)P * g.S * 3);
+        if (PEER) {
+          if (xlo != nullptr && P == 0) pp = reinterpret_cast<const char*>(xlo);
+          if (xhi != nullptr && P == g.nown + 1) pp = reinterpret_cast<const char*>(xhi);
+        }
+#pragma unroll
+        for (int q = 0; q < JPL; ++q) {
+          if (jvalid[q]) {
+            const int w = jw[q];
+            if (fcount >= NST) {
+              while (!mbar_try_wait(&empty[w][s], rel_par)) {
+              }
+            }
+            uint64_t* bar = &full[w][s];
+            if (jok[q]) {
+              const char* a = pp + jidx[q];
+              const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(a) & 15);
+              const uint32_t nb = (lead + jbytes + 15u) & ~15u;
+              mbar_arrive_expect_tx(bar, nb);
+              bulk_g2s(smem_raw + jdst[q] + s * kRingStage, a - lead, nb, bar);
+            } else {
+              mbar_arrive(bar);
+            }
+          }
         }
       }
-      mbar_arrive_expect_tx(&full[stg], total);
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-        if (nb[k]) bulk_g2s(sbase + (2 * ty + k) * kRingPitch + dst_off, src[k], nb[k], &full[stg]);
-    };
-    // raw values of this lane's node and its x+1 neighbour in rows A, B, C of plane P
-    auto read_plane = [&](int P, double (&ow)[3][3], double (&rt)[3][3]) {
-      const unsigned f = fbase + (unsigned)(P - first);
-      const int stg = (int)(f % NST);
-      const uint32_t par = (f / NST) & 1u;
-      while (!mbar_try_wait(&full[stg], par)) {
-      }
-      const unsigned pl = (unsigned)(reinterpret_cast<uintptr_t>(plane_ptr(P)) & 8);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const double* q = reinterpret_cast<const double*>(ring + stg * STAGE + base_off[k] + (int)(pl ^ rowpar[k]));
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          ow[k][c] = q[c];
-          rt[k][c] = q[3 + c];
-        }
-      }
-    };
-    auto load_E = [&](int k, int ll) -> double {
-      const int gl = ll + g.p0;
-      return (el_ok[k] && gl >= 0 && gl < g.NLg) ? E[(long long)ll * g.SE + ecol[k]] : 0.0;
-    };
-
-    // ---- prologue: fill the ring, x stage of the first plane
-    const int nplanes = zlen + 2;
-    if (tx == 0) {
-      for (int f = 0; f < NST && f < nplanes; ++f) issue_fill(first + f, fbase + (unsigned)f);
     }
-    __syncwarp();
-    double pa[3][3], pe[3][3];  // x-staged previous plane, rows A, B, C
-    {
-      double ow[3][3], rt[3][3];
-      read_plane(first, ow, rt);
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          pa[k][c] = rt[k][c] + ow[k][c];
-          pe[k][c] = rt[k][c] - ow[k][c];
-        }
-    }
-    double carry[2][3];
-#pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) carry[r][c] = 0.0;
-    double En[2] = {load_E(0, first), load_E(1, first)};
-
-    // deferred tail state: x-reduced corner forces of rows A, B of the previous step
-    double nA[2][3], nB[2][3];
-    int par = 0;
-
-    // tail of step L: y reduction, inverse z stage, store of plane L, refill of plane L's ring stage
-    auto tail = [&](int L, int parL) {
-      {
-        const int lo = ty > 0 ? ty - 1 : 0, hi = ty + 1 < TYT ? ty + 1 : TYT - 1;
+  } else {
+    // =========================== compute warps ===========================
+    unsigned char* ring = smem_raw + ty * WRING;  // this warp's ring
+    int it = 0;          // published-step counter (monotonic across segments)
+    int seg = 0;         // segment counter
+    int sf = 0;          // ring stage of the next plane to be consumed
+    unsigned phase = 0;  // bit s: parity to wait for on full[ty][s]
+    auto next_stage = [](int s) { return s + 1 == NST ? 0 : s + 1; };
+    while (u0 < u1) {
+      const int tile = (int)(u0 / g.nown);
+      const int zoff = (int)(u0 % g.nown);
+      const int zlen = (int)min((long long)(g.nown - zoff), u1 - u0);
+      u0 += zlen;
+      const int bx = tile % tilesX, by = tile / tilesX;
+      const int c0 = bx * 31 - 1, r0 = by * OWNR - 1 + 2 * ty;  // node column of lane 0 / node row of this warp's row A
+      const int z0 = 1 + zoff, z1 = z0 + zlen;                  // owned local planes [z0, z1); planes z0-1 .. z1 are read
+      const int first = z0 - 1;
+      const int c_lo = max(c0, 0);
+      const int shift = c_lo - c0;  // 1 on the left-edge tile (column -1 does not exist)
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * TYT) : "memory");  // compute warps only: the previous segment's yb reads are complete
+      // Stagger the thread rows: a row starts a segment only after the row below has finished the forward
+      // stage of its first step.  All warps run the same code at the same pace, so without this the fp64-bound
+      // and the latency-bound parts of a step coincide on all warps of an SM sub-partition; the skew persists
+      // (a row never waits while it lags) and costs (TYT-1) x 1/6 step per ~50-step segment.
+      ++seg;
+      if (STAGGER && ty > 0) {
         int spins = 0;
         bool ready;
         do {
-          ready = (*(volatile int*)&sflag[lo] >= it && *(volatile int*)&sflag[hi] >= it) || ++spins > (1 << 24);
+          ready = *(volatile int*)&sstart[ty - 1] >= seg || ++spins > (1 << 24);
         } while (!__all_sync(FULL, ready));
-        __threadfence_block();
       }
-      if (ty >= 1) {
+
+      const int col = c0 + tx;
+      // byte offsets of this lane's slot inside a node / E / flag row (before the alignment lead)
+      const int lane_off = (shift ? 32 - 24 : 0) + 24 * tx;
+      bool node_ok[2], own[2], el_ok[2];
+      int ncol[2], ecol[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int r = r0 + k;
+        node_ok[k] = col >= 0 && col < g.NX && r >= 0 && r < g.NY;
+        el_ok[k] = col >= 0 && col < g.nx && r >= 0 && r < g.ny;
+        ncol[k] = node_ok[k] ? r * g.NX + col : 0;
+        ecol[k] = el_ok[k] ? r * g.nx + col : 0;
+      }
+      own[0] = node_ok[0] && tx >= 1 && ty >= 1;  // row A of thread row 0 lacks the tile below
+      own[1] = node_ok[1] && tx >= 1;             // lane 0 lacks the element column to its left
+      // alignment leads (address & 15) of the copied rows; the plane-dependent part is added per step
+      const unsigned leadN0 = (unsigned)(((long long)r0 * g.NX + c_lo) & 1) << 3;  // rows A, C
+      const unsigned leadNB = leadN0 ^ ((unsigned)(g.NX & 1) << 3);                // row B
+
+      auto plane_lead = [&](int P) -> unsigned {
+        const char* pp = reinterpret_cast<const char*>(x + (long long)P * g.S * 3);
+        if (PEER) {
+          if (xlo != nullptr && P == 0) pp = reinterpret_cast<const char*>(xlo);
+          if (xhi != nullptr && P == g.nown + 1) pp = reinterpret_cast<const char*>(xhi);
+        }
+        return (unsigned)(reinterpret_cast<uintptr_t>(pp) & 8);
+      };
+      // `hint`: result of a test issued one step earlier (its latency is hidden behind that step's work)
+      auto wait_stage = [&](int s, bool hint) {
+        const uint32_t par = (phase >> s) & 1u;
+        if (!__all_sync(FULL, hint)) {
+          bool landed;
+          do {
+            landed = mbar_try_wait(&full[ty][s], par);
+          } while (!__all_sync(FULL, landed));
+        }
+        phase ^= 1u << s;
+      };
+      auto test_stage = [&](int s) -> bool { return mbar_test_wait(&full[ty][s], (phase >> s) & 1u); };
+      auto release_stage = [&](int s) {
+        __syncwarp();
+        if (tx == 0) mbar_arrive(&empty[ty][s]);
+      };
+      // x stage of rows A, B, C of the plane held in stage s: a = x+1 + own, e = x+1 - own
+      auto xstage = [&](int s, unsigned pl, double (&a)[3][3], double (&e)[3][3]) {
+        const unsigned char* base = ring + s * kRingStage + lane_off;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double* q = reinterpret_cast<const double*>(base + k * kRingPitch + (int)(pl ^ (k == 1 ? leadNB : leadN0)));
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const double o = q[c], r = q[3 + c];
+            a[k][c] = r + o;
+            e[k][c] = r - o;
+          }
+        }
+      };
+
+      int s_tail = sf, s_old = sf, s_new = next_stage(sf);  // stages of planes ll - 1 (tail), ll, ll + 1 at step ll
+      wait_stage(s_old, false);  // the first plane only serves as the bottom plane of the first layer
+      bool hint_new = false;
+      double carry[2][3], nA[2][3], nB[2][3];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) carry[r][c] = nA[r][c] = nB[r][c] = 0.0;
+      double* yp[2] = {y + ((long long)(first - 1) * g.S + ncol[0]) * 3, y + ((long long)(first - 1) * g.S + ncol[1]) * 3};
+      const long long ystep = (long long)g.S * 3;
+      // E_e of the layer and prescribed-dof flags of its bottom plane: plain loads, one step ahead
+      const double* Ep[2] = {E + (long long)first * g.SE + ecol[0], E + (long long)first * g.SE + ecol[1]};
+      const unsigned char* fp[2] = {fixed + (long long)first * g.S + ncol[0], fixed + (long long)first * g.S + ncol[1]};
+      auto layer_ok = [&](int ll) -> bool {
+        const int gl = ll + g.p0;
+        return gl >= 0 && gl < g.NLg;
+      };
+      double En[2];
+      unsigned char flg[2] = {0, 0}, fln[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        En[k] = (el_ok[k] && layer_ok(first)) ? Ep[k][0] : 0.0;
+        fln[k] = node_ok[k] ? fp[k][0] : 0;
+      }
+      int par = 0, hi_seen = 0;
+
+      // tail of step L: y reduction, inverse z stage, store of plane L, release of plane L's ring stage.
+      // It only depends on the thread row BELOW (its row C partial sums of step L), so the rows form a
+      // one-directional chain and settle into a staggered wavefront instead of meeting at every step.
+      // Called with L = first - 1 before the first step: a no-op (nothing stored, carry is overwritten by the
+      // next call before it is used).
+      auto tail = [&](int L, int parL) {
+        {
+          const int lo = ty > 0 ? ty - 1 : 0;
+          int spins = 0;
+          bool ready;
+          do {
+            ready = *(volatile int*)&sflag[lo] >= it || ++spins > (1 << 24);
+          } while (!__all_sync(FULL, ready));
+          __threadfence_block();
+        }
+        // the row above must have consumed the y buffer this step will overwrite (written three steps ago):
+        // true once it has published step it - 2; read here, early, tested right before the stores
+        hi_seen = *(volatile int*)&sflag[ty + 1 < TYT ? ty + 1 : ty];
+        const bool store = L >= z0;
+        // raw x (prescribed rows, dot products) and flags of the plane being stored: still in the ring
+        const unsigned pl = plane_lead(L);
+        const unsigned char* sb = ring + s_tail * kRingStage;
 #pragma unroll
         for (int m = 0; m < 2; ++m)
 #pragma unroll
-          for (int c = 0; c < 3; ++c) nA[m][c] += yb[parL][3 * m + c][ty - 1][tx];
-      }
-      if (L >= z0) {
-        // raw x of the plane being stored (prescribed rows, dot products): still in the ring
-        const unsigned f = fbase + (unsigned)(L - first);
-        const int stg = (int)(f % NST);
-        const unsigned pl = (unsigned)(reinterpret_cast<uintptr_t>(plane_ptr(L)) & 8);
+          for (int c = 0; c < 3; ++c) nA[m][c] += yb[parL][3 * m + c][ty][tx];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           double(&n)[2][3] = r == 0 ? nA : nB;
-          const double* q = reinterpret_cast<const double*>(ring + stg * STAGE + base_off[r] + (int)(pl ^ rowpar[r]));
-          const unsigned char fl = node_ok[r] ? fixed[(long long)L * g.S + ncol[r]] : 0;
-          if (own[r]) {
-            const long long yo = ((long long)L * g.S + ncol[r]) * 3;
+          const double* q = reinterpret_cast<const double*>(sb + lane_off + r * kRingPitch + (int)(pl ^ (r == 1 ? leadNB : leadN0)));
+          const unsigned char fl = flg[r];
+          const bool st_ok = store && own[r];
+          double xo[3], v[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            xo[c] = q[c];
+            v[c] = carry[r][c] + (n[0][c] - n[1][c]);
+            carry[r][c] = n[0][c] + n[1][c];
+            if (fl & (1 << c)) v[c] = fixed_diag * xo[c];  // prescribed row: meandiag * x
+          }
+          if (st_ok) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              const double xo = q[c];
-              double v = carry[r][c] + (n[0][c] - n[1][c]);
-              if (fl & (1 << c)) v = fixed_diag * xo;  // prescribed row: meandiag * x
-              y[yo + c] = v;
-              if (DOT >= 1) dots[0] = fma(xo, v, dots[0]);
-              if (DOT == 2) dots[1] = fma(v, v, dots[1]);
+              yp[r][c] = v[c];
+              if (DOT >= 1) dots[0] = fma(xo[c], v[c], dots[0]);
+              if (DOT == 2) dots[1] = fma(v[c], v[c], dots[1]);
             }
           }
+          yp[r] += ystep;
         }
-      }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        carry[0][c] = nA[0][c] + nA[1][c];
-        carry[1][c] = nB[0][c] + nB[1][c];
-      }
-      // plane L is no longer needed by this thread row nor (as its row C) by the row below: refill its stage
-      if (L + NST <= last) {
-        if (tx == 0) issue_fill(L + NST, fbase + (unsigned)(L + NST - first));
-        __syncwarp();
-      }
-    };
+        // plane L has been consumed by this warp (nobody else reads its ring): hand the stage back
+        if (L >= first) release_stage(s_tail);
+      };
 
-    for (int ll = first; ll < z1; ++ll, par ^= 1) {  // element layer ll: planes ll (bottom), ll + 1 (top)
-      double ow[3][3], rt[3][3];
-      read_plane(ll + 1, ow, rt);
-      const double Ee[2] = {En[0], En[1]};
-      if (ll + 1 < z1) {
-        En[0] = load_E(0, ll + 1);
-        En[1] = load_E(1, ll + 1);
-      }
-      if (ll > first) tail(ll - 1, par ^ 1);
-      RowX xa, xb, xc;
-      hex8_zstage(ow[0], rt[0], pa[0], pe[0], xa);
-      hex8_zstage(ow[1], rt[1], pa[1], pe[1], xb);
-      hex8_zstage(ow[2], rt[2], pa[2], pe[2], xc);
-      // ---- the two elements; E-scaled accumulation onto the x edges of rows A, B, C
-      double WA[2][2][3], WB[2][2][3], WC[2][2][3];
-      {
-        double wL[2][2][3], wU[2][2][3];
-        hex8_core(xa, xb, wL, wU);
+      for (int ll = first; ll < z1; ++ll, par = par == 2 ? 0 : par + 1) {  // element layer ll: planes ll (bottom), ll + 1 (top)
+        wait_stage(s_new, hint_new);
+        hint_new = test_stage(next_stage(s_new));  // next step's plane: usually landed already
+        tail(ll - 1, par == 0 ? 2 : par - 1);
+        const double Ee[2] = {En[0], En[1]};
 #pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-          for (int m = 0; m < 2; ++m)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              WA[a][m][c] = Ee[0] * wL[a][m][c];
-              WB[a][m][c] = Ee[0] * wU[a][m][c];
-            }
-      }
-      {
-        double wL[2][2][3], wU[2][2][3];
-        hex8_core(xb, xc, wL, wU);
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-          for (int m = 0; m < 2; ++m)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              WB[a][m][c] = fma(Ee[1], wL[a][m][c], WB[a][m][c]);
-              WC[a][m][c] = Ee[1] * wU[a][m][c];
-            }
-      }
-      // ---- inverse x stage per x edge, reduction over x by shuffle; row C goes to the thread row above
-#pragma unroll
-      for (int m = 0; m < 2; ++m)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          nA[m][c] = (WA[0][m][c] - WA[1][m][c]) + __shfl_up_sync(FULL, WA[0][m][c] + WA[1][m][c], 1);
-          nB[m][c] = (WB[0][m][c] - WB[1][m][c]) + __shfl_up_sync(FULL, WB[0][m][c] + WB[1][m][c], 1);
-          yb[par][3 * m + c][ty][tx] = (WC[0][m][c] - WC[1][m][c]) + __shfl_up_sync(FULL, WC[0][m][c] + WC[1][m][c], 1);
+        for (int k = 0; k < 2; ++k) {
+          flg[k] = fln[k];  // flags of plane ll: used by tail(ll) one step later
+          Ep[k] += g.SE;
+          fp[k] += g.S;
+          En[k] = (el_ok[k] && ll + 1 < z1 && layer_ok(ll + 1)) ? Ep[k][0] : 0.0;
+          fln[k] = node_ok[k] ? fp[k][0] : 0;
         }
-      ++it;
-      __syncwarp();
-      if (tx == 0) {
-        __threadfence_block();
-        *(volatile int*)&sflag[ty] = it;
+        // ---- forward x and z stages of rows A, B, C from the raw planes ll and ll + 1
+        RowX xr[3];
+        {
+          double ab[3][3], eb[3][3], at[3][3], et[3][3];
+          xstage(s_old, plane_lead(ll), ab, eb);
+          xstage(s_new, plane_lead(ll + 1), at, et);
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              xr[k].ss[c] = at[k][c] + ab[k][c];
+              xr[k].sd[c] = at[k][c] - ab[k][c];
+              xr[k].ds[c] = et[k][c] + eb[k][c];
+              xr[k].dd[c] = et[k][c] - eb[k][c];
+            }
+        }
+        if (STAGGER && ll == first) {
+          __syncwarp();
+          if (tx == 0) *(volatile int*)&sstart[ty] = seg;
+        }
+        // ---- the two elements; E-scaled accumulation onto the x edges of rows A, B, C
+        double WA[2][2][3], WB[2][2][3], WC[2][2][3];
+        {
+          double wL[2][2][3], wU[2][2][3];
+          hex8_core(xr[0], xr[1], wL, wU);
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                WA[a][m][c] = Ee[0] * wL[a][m][c];
+                WB[a][m][c] = Ee[0] * wU[a][m][c];
+              }
+        }
+        {
+          double wL[2][2][3], wU[2][2][3];
+          hex8_core(xr[1], xr[2], wL, wU);
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                WB[a][m][c] = fma(Ee[1], wL[a][m][c], WB[a][m][c]);
+                WC[a][m][c] = Ee[1] * wU[a][m][c];
+              }
+        }
+        // ---- inverse x stage per x edge, reduction over x by shuffle; row C goes to the thread row above.
+        // The y buffer written now (one of three) was last read by the row above in its tail of step ll - 3, which
+        // precedes its publication of step ll - 2: normally known from the flag value read at the top of the step.
+        if (!__all_sync(FULL, hi_seen >= it - 1)) {
+          const int hi = ty + 1 < TYT ? ty + 1 : ty;
+          int spins = 0;
+          bool ready;
+          do {
+            ready = *(volatile int*)&sflag[hi] >= it - 1 || ++spins > (1 << 24);
+          } while (!__all_sync(FULL, ready));
+        }
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            nA[m][c] = (WA[0][m][c] - WA[1][m][c]) + __shfl_up_sync(FULL, WA[0][m][c] + WA[1][m][c], 1);
+            nB[m][c] = (WB[0][m][c] - WB[1][m][c]) + __shfl_up_sync(FULL, WB[0][m][c] + WB[1][m][c], 1);
+            yb[par][3 * m + c][ty + 1][tx] = (WC[0][m][c] - WC[1][m][c]) + __shfl_up_sync(FULL, WC[0][m][c] + WC[1][m][c], 1);
+          }
+        ++it;
+        __syncwarp();
+        if (tx == 0) {
+          __threadfence_block();
+          *(volatile int*)&sflag[ty] = it;
+        }
+        s_tail = s_old;
+        s_old = s_new;
+        s_new = next_stage(s_new);
       }
-    }
-    tail(z1 - 1, par ^ 1);
-    fbase += (unsigned)nplanes;
-  }  // segments
+      tail(z1 - 1, par == 0 ? 2 : par - 1);
+      release_stage(s_old);  // the top plane of the last layer was only read as a "new" plane
+      sf = s_new;
+    }  // segments
+  }
   if (DOT) block_partials_finish<NS>(dots, partials, st, fin, sm);
 }
 
