@@ -39,3 +39,28 @@ def test_native_arm_refuses_to_run_without_a_gpu():
     assert out.returncode != 0
     assert out.stdout.strip() == ""  # no JSON line is fabricated
     assert "CUDA" in out.stderr or "cuda" in out.stderr
+
+
+def test_reference_arm_is_independent_of_the_product_and_of_torchrun_thread_limits():
+    """the reference arm builds its inputs from oracle/ only (the product package and its
+    CUDA library are never imported) and uses every host core even when the launcher exports
+    OMP_NUM_THREADS=1 (torchrun does); it also reports one COMPLETE config-3 step next to the extrapolated one."""
+    code = (
+        "import sys, json, io, os\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "sys.argv = ['bench.py', '--impl', 'reference', '--nels', '12,4,4', '--steps', '1', '--warmup', '1', '--ref-cg-iters', '2']\n"
+        "import bench\n"
+        "bench.main()\n"
+        "bad = [m for m in sys.modules if m.startswith('topopt_jl_b200') or m == 'torch']\n"
+        "maps = open('/proc/self/maps').read()\n"
+        "sys.stderr.write('LOADED=' + json.dumps(bad) + ' CUDA_SO=' + str('libtopopt_cuda' in maps) + '\\n')\n"
+    )
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "LOADED=[] CUDA_SO=False" in out.stderr, out.stderr[-500:]
+    d = json.loads([ln for ln in out.stdout.splitlines() if ln.strip()][0])
+    ncpu = len(os.sched_getaffinity(0))
+    assert d["cpu_baseline"]["cores"] == ncpu == d["host_threads"]
+    full = d["config3_full_step"]
+    assert full["cg_iters"] > 0 and full["it_per_s"] > 0 and "60x20x20" in full["workload"]
