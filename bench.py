@@ -336,7 +336,7 @@ def run_native(args, nels):
     # ---- dominant kernel: K.u as the CG loop launches it, CUDA events on the library's stream -------------
     single = args.cg_variant == 1 and world == 1 or (args.cg_variant == 1 and comm is not None and getattr(comm, "peer_memory", True))
     nown = nels[2] // world + (1 if world == 1 else 0)
-    ring = nown >= 24 and os.environ.get("TOPOPT_KXU_RING", "1") != "0" and (world == 1 or os.environ.get("TOPOPT_KXU_RING_PEER", "1") != "0")
+    ring = nown >= int(os.environ.get("TOPOPT_KXU_RING_MIN", "12")) and os.environ.get("TOPOPT_KXU_RING", "1") != "0"
     kxu_which = 8 if (single and ring) else 0
     kxu_ms = solver.time_kernel(kxu_which, args.kernel_reps)
     cg_ms = solver.time_kernel(9 if single and ring else 1, args.kernel_reps)

@@ -216,6 +216,10 @@ int topopt_swap_solution_lambda(topopt_handle* h);
  * getcompliance).  a NULL = fixedload, b NULL = resident u. */
 int topopt_dot(topopt_handle* h, const double* a, const double* b, double* out);
 
+/* FEA.getcompliance (src/FEA/FEA.jl:40): u' K u with the current stiffness, evaluated on the device.
+ * u NULL = the device-resident solution. */
+int topopt_quadratic_form(topopt_handle* h, const double* u, double* out);
+
 /* ---- filters (src/CheqFilters) -------------------------------------------------------- */
 /* FilterMetadata + getJacobian (CheqFilters.jl:66-118, density_filter.jl:49-108) without
  * materialising J: two-stage cell->node->cell stencil with the reference's duplicate weights. */

@@ -52,6 +52,34 @@ def main():
         of, _, gf = o.compliance(oprob, uf, xf, 3.0, 1e-3)
         assert abs(objf - of) / of < 1e-8 and rel(gx, Fo.pullback(gf)) < 1e-8
         F.close(); s.close(); s2.close()
+    # thick slabs (>= 100 node planes per rank): the kernels selected for the large configurations, with their
+    # peer-memory halo reads -- ring-staged (bulk copies straight from the neighbours' memory) and, with the ring
+    # kernel disabled, the two-row shuffle kernel; both CG recurrences
+    nels = (8, 4, 100 * comm.world)
+    prob, oprob = t.PointLoadCantilever(nels), o.PointLoadCantilever(nels)
+    prob.Ke = oprob.Ke.copy()
+    rho = np.random.default_rng(7).uniform(0.2, 1.0, prob.nel)
+    E = o.get_rho(rho, 3.0, 1e-3)
+    uref = o.solve_direct(oprob, E)
+    obj, cc, g = o.compliance(oprob, uref, rho, 3.0, 1e-3)
+    uo, it, res = o.solve_matfree(oprob, E, abstol=0.0, reltol=0.0, maxiter=10)
+    for env in ({}, {"TOPOPT_KXU_RING": "0"}):
+        os.environ.update(env)
+        for variant in (0, 1):
+            s = t.FEASolver(t.CUDAMatrixFreeSolver, prob, penalty=t.PowerPenaltyFun(3.0), abstol=1e-12, reltol=1e-14,
+                            cg_max_iter=50000, device=local, comm=comm, cg_variant=variant)
+            comp = t.ComplianceFun(s)
+            val, grad = comp.value_and_grad(rho)
+            assert s.last_result.converged == 1, (env, variant)
+            assert abs(val - obj) / obj < 1e-8 and rel(grad, g) < 1e-8 and rel(s.u, uref) < 1e-7, (env, variant, abs(val - obj) / obj)
+            s2 = t.FEASolver(t.CUDAMatrixFreeSolver, prob, penalty=t.PowerPenaltyFun(3.0), abstol=0.0, reltol=0.0,
+                             cg_max_iter=10, device=local, comm=comm, cg_variant=variant)
+            s2.vars = rho
+            u10 = s2().copy()
+            assert s2.last_result.iters == 10 and rel(u10, uo) < 1e-9, (env, variant, rel(u10, uo))
+            s.close(); s2.close()
+        for k in env:
+            os.environ.pop(k, None)
     import torch.distributed as dist
 
     dist.barrier()

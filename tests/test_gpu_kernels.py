@@ -247,3 +247,90 @@ def test_config4_full_size_against_c_port(lib):
         assert abs(s.last_result.residual - res) <= 1e-9 * res
     R.close()
     s.close()
+
+
+def test_plain_c_harness_drives_the_abi(lib, tmp_path):
+    """The boundary is a C ABI: a plain C99 program (tests/c/harness.c) creates the handle, sets the density,
+    solves, evaluates compliance / sensitivities / u'Ku, filters and runs the fused SIMP evaluation -- on every
+    visible device (up to two, one handle each in the same process: per-device kernel attributes) -- and its
+    numbers must match the oracle."""
+    import subprocess
+
+    import torch
+
+    t = lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "topopt.jl_b200")
+    exe = tmp_path / "harness"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-O1", "-I", os.path.join(root, "include"),
+           os.path.join(root, "tests", "c", "harness.c"), "-o", str(exe), "-L", libdir, "-ltopopt_cuda", f"-Wl,-rpath,{libdir}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    ndev = min(2, torch.cuda.device_count())
+    out = subprocess.run([str(exe), str(ndev)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    nels = (12, 4, 28)
+    oprob = o.PointLoadCantilever(nels)
+    ne = oprob.nel
+    e = np.arange(ne, dtype=np.uint64)
+    rho = 0.2 + 0.8 * ((e * np.uint64(2654435761)) % np.uint64(1000)).astype(np.float64) / 1000.0
+    E = o.get_rho(rho, 3.0, 1e-3)
+    uref = o.solve_direct(oprob, E)
+    obj, _, g = o.compliance(oprob, uref, rho, 3.0, 1e-3)
+    Fo = o.DensityFilter(oprob, 2.0)
+    xf = Fo(rho)
+    uf = o.solve_direct(oprob, o.get_rho(xf, 3.0, 1e-3))
+    obj_f, _, _ = o.compliance(oprob, uf, xf, 3.0, 1e-3)
+    lines = [ln.split() for ln in out.stdout.strip().splitlines()]
+    assert len(lines) == ndev
+    for ln in lines:
+        vals = [float(v) for v in ln[1:]]
+        assert abs(vals[0] - obj) / obj < 1e-8
+        assert abs(vals[1] - obj_f) / obj_f < 1e-8
+        assert abs(vals[2] - float(g @ (1 + np.arange(ne) % 7))) <= 1e-8 * float(np.abs(g) @ (1 + np.arange(ne) % 7))
+        assert abs(vals[3] - float(xf @ (1 + np.arange(ne) % 5))) <= 1e-12 * float(xf @ (1 + np.arange(ne) % 5))
+        assert abs(vals[5] - obj) / obj < 1e-8  # u'Ku == sum E_e u_e'Ke u_e
+
+
+@pytest.mark.parametrize("kind", ["displacement", "temperature"])
+def test_displacement_and_temperature_fun_adjoints(lib, kind):
+    """DisplacementFun / TemperatureFun (displacement.jl:97-121, temperature.jl:92-119): the value is
+    the solved field; the pullback of a cotangent delta is one adjoint solve K lam = delta (arbitrary right-hand side,
+    apply_zero!) and out_e = -dE_e u_e' Ke lam_e.  Checked against the oracle and against a finite difference."""
+    t = lib
+    if kind == "displacement":
+        nels = (10, 4, 6)
+        prob, oprob = t.PointLoadCantilever(nels), o.PointLoadCantilever(nels)
+        Fun = t.DisplacementFun
+    else:
+        nels = (12, 9)
+        prob, oprob = t.HeatTree(nels), o.HeatTree(nels)
+        Fun = t.TemperatureFun
+    prob.Ke = oprob.Ke.copy()
+    s = t.FEASolver(t.CUDAMatrixFreeSolver, prob, penalty=t.PowerPenaltyFun(3.0), abstol=1e-13, reltol=1e-15, cg_max_iter=50000)
+    f = Fun(s)
+    rho = rand_rho(prob.nel, 3)
+    u = f(rho)
+    E, dE = o.get_rho_drho(rho, 3.0, 1e-3)
+    uref = o.solve_direct(oprob, E)
+    assert rel(u, uref) < 1e-8
+    delta = np.random.default_rng(8).standard_normal(prob.ndof)
+    g = f.pullback(delta)
+    lam = o.solve_direct(oprob, E, rhs=delta)
+    gref = -dE * o.element_energy(oprob, uref, lam)
+    assert rel(g, gref) < 1e-8
+    # directional finite difference of delta . u(rho)
+    d = np.random.default_rng(9).standard_normal(prob.nel)
+    h = 1e-6
+    up = o.solve_direct(oprob, o.get_rho(rho + h * d, 3.0, 1e-3))
+    um = o.solve_direct(oprob, o.get_rho(rho - h * d, 3.0, 1e-3))
+    fd = float(delta @ (up - um)) / (2 * h)
+    free = np.ones(prob.ndof, dtype=bool)
+    free[oprob.prescribed] = False
+    fd_free = float(delta[free] @ (up - um)[free]) / (2 * h)
+    assert abs(float(g @ d) - fd_free) <= 1e-5 * max(abs(fd_free), 1e-12)
+    # wrong physics is an ArgumentError in the reference
+    Other = t.TemperatureFun if kind == "displacement" else t.DisplacementFun
+    with pytest.raises(ValueError):
+        Other(s)
+    s.close()

@@ -19,7 +19,7 @@ from .fea import (
     SinhPenaltyFun,
     getcompliance,
 )
-from .functions import ComplianceFun, ThermalComplianceFun, VolumeFun
+from .functions import ComplianceFun, DisplacementFun, TemperatureFun, ThermalComplianceFun, VolumeFun
 from .problems import HalfMBB, HeatConductionProblem, HeatTree, Metadata, PointLoadCantilever, element_matrix
 from .simp import oc_update, simp_eval, simp_loop
 

@@ -123,6 +123,7 @@ SIGNATURES = {
     "topopt_bilinear_sens": (C.c_int, [VP, VP, VP, VP, VP]),
     "topopt_swap_solution_lambda": (C.c_int, [VP]),
     "topopt_dot": (C.c_int, [VP, VP, VP, c_dp]),
+    "topopt_quadratic_form": (C.c_int, [VP, VP, c_dp]),
     "topopt_filter_create": (C.c_int, [VP, C.c_double, C.POINTER(VP)]),
     "topopt_filter_apply": (C.c_int, [VP, VP, VP, C.c_int32]),
     "topopt_filter_destroy": (C.c_int, [VP]),

@@ -82,7 +82,7 @@ struct topopt_handle {
   int kxu_ty = 16, kxu_waves = 1, kxu_nsync = 1, kxu_2row = 1;  // 2row: 0 = one-row kernel, 1 = auto, else thread rows
   int kxu_ring = 1;       // ring-staged kernel for premasked inputs (CG directions): 0 = off, 1 = auto, else thread rows
   int kxu_stagger = 0;    // ring kernel: stagger the thread rows at segment starts
-  int kxu_ring_min = 24;  // fewest owned node planes per rank for which the ring kernel is selected
+  int kxu_ring_min = 12;  // fewest owned node planes per rank for which the ring kernel is selected
   int cg_variant_env = -1;  // TOPOPT_CG_VARIANT overrides topopt_cg_opts.variant (diagnostics)
   double fixed_diag = 0.0, cellvol = 1.0;
   double sizes[3] = {1, 1, 1};
@@ -604,7 +604,8 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
       if (single) {  // K.u (+ p.Ap, Ap.Ap -> alpha, beta) ; x, r, p in one pass (+ r.r)
         TRY(launch_cg_apply<2>(h, peer_halo, FIN_PAP2));
         mark();
-        LAUNCH(h, k_update_xrp, vgrid, h->off, h->nown_dofs, h->d_u, h->d_r, h->d_p, h->d_Ap, h->d_partials, h->d_st, peer_halo ? 1 : 0);
+        LAUNCH(h, k_update_xrp, vgrid, h->off, h->nown_dofs, h->d_u, h->d_r, h->d_p, h->d_Ap, h->d_partials, h->d_st,
+               peer_halo ? (long long)h->plane_dofs : 0ll);
         launches_per_iter = 2;
         return TOPOPT_OK;
       }
@@ -645,6 +646,13 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
       launches_per_iter = 3;
       return TOPOPT_OK;
     };
+    // multi-GPU single-pass recurrence: the last iteration's r.r is posted but not collected yet
+    auto flush_batch = [&]() {
+      if (single && peer) {
+        k_cg_flush<<<1, 32, 0, h->stream>>>(h->d_st);
+        h->stats.kernel_launches += 1;
+      }
+    };
     // Replay a captured graph of n iterations when nothing in the batch depends on host state:
     // single GPU or the peer-memory path (no NCCL calls inside), no fused pointer swap, no tracing.
     const bool graphable = h->use_graphs && !trace && !fusep && (h->world == 1 || (peer && (peer_halo || assembled))) && issued > 0;
@@ -667,12 +675,14 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
         CUDA_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         int rc = TOPOPT_OK;
         for (int it = 0; it < n && rc == TOPOPT_OK; ++it) rc = one_iteration();
+        if (rc == TOPOPT_OK) flush_batch();
         cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
         if (rc != TOPOPT_OK || ce != cudaSuccess || graph == nullptr) {
           if (graph) cudaGraphDestroy(graph);
           cudaGetLastError();
           h->use_graphs = false;  // fall back to plain launches from now on
           for (int it = 0; it < n; ++it) TRY(one_iteration());
+          flush_batch();
         } else {
           ce = cudaGraphInstantiate(&h->cg_graph, graph, 0);
           cudaGraphDestroy(graph);
@@ -681,6 +691,7 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
             h->use_graphs = false;
             cudaGetLastError();
             for (int it = 0; it < n; ++it) TRY(one_iteration());
+            flush_batch();
           } else {
             h->cg_graph_key = key;
             h->cg_graph_launches = (long long)n * launches_per_iter;
@@ -693,6 +704,7 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
       }
     } else {
       for (int it = 0; it < n; ++it) TRY(one_iteration());
+      flush_batch();
     }
     if (trace && issued == 0 && !tev.empty()) {
       mark();
@@ -1384,6 +1396,33 @@ int topopt_dot(topopt_handle* h, const double* a, const double* b, double* out) 
   }
   LAUNCH(h, k_dot, kReduceBlocks, h->off, h->nown_dofs, da, db, h->d_partials, h->d_st);
   TRY(check_launch(h, "k_dot"));
+  if (h->world > 1)
+    NCCL_TRY(h, g_nccl.AllReduce(h->d_st->sums, h->d_st->sums, 1, ncclDouble, ncclSum, h->comm, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_st, h->d_st, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  TRY(sync(h));
+  *out = h->h_st->sums[0];
+  return TOPOPT_OK;
+}
+
+// u' K u with the current stiffness (FEA.getcompliance, src/FEA/FEA.jl:40); u NULL = resident solution
+int topopt_quadratic_form(topopt_handle* h, const double* u, double* out) {
+  if (!h || !out) return fail(h, TOPOPT_ERR_INVALID, "topopt_quadratic_form: NULL argument");
+  TRY(use_device(h));
+  if (u) {
+    TRY(upload_dofs(h, u, h->d_p));
+  } else {
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_p, h->d_u, sizeof(double) * h->nloc_dofs, cudaMemcpyDeviceToDevice, h->stream));
+    TRY(exchange_halo(h, h->d_p));
+  }
+  CGState zero;
+  std::memset(&zero, 0, sizeof(zero));
+  zero.world = 1;
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_st, &zero, sizeof(CGState), cudaMemcpyHostToDevice, h->stream));
+  if (h->assembled && !h->stiffness_dirty && h->world == 1) {
+    TRY(launch_spmv<true>(h, h->d_p, h->d_Ap, FIN_NONE));
+  } else {
+    TRY(launch_apply<true>(h, h->d_p, h->d_Ap, FIN_NONE));
+  }
   if (h->world > 1)
     NCCL_TRY(h, g_nccl.AllReduce(h->d_st->sums, h->d_st->sums, 1, ncclDouble, ncclSum, h->comm, h->stream));
   CUDA_TRY(h, cudaMemcpyAsync(h->h_st, h->d_st, sizeof(double), cudaMemcpyDeviceToHost, h->stream));

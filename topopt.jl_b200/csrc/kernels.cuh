@@ -32,7 +32,7 @@ constexpr int kMaxRanks = 8;
 struct PeerBlock {
   // [parity][source rank][scalar] = (value, sequence number): every scalar travels with its own
   // sequence tag in ONE aligned 16-byte store, so the receiver needs neither a fence nor a flag
-  double2 slots[2][kMaxRanks][8];
+  double2 slots[4][kMaxRanks][8];           // four-deep: a deferred value stays valid until its collector has run
   unsigned long long halo_flag[2];          // [0]: written by the rank below, [1]: by the rank above
 };
 
@@ -50,7 +50,9 @@ struct CGState {
   double res, prev_res, rho, rho_prev, alpha, beta, tol, abstol, reltol, energy, pAp;
   int iters, done, converged, maxiter, criteria, precond, nonfinite, world;
   int variant;      // 0 = IterativeSolvers recurrence, 1 = single-pass recurrence (FIN_PAP2 / FIN_RR2)
-  unsigned int counter;
+  int rr_pending;   // multi-GPU single-pass: this rank's r.r is posted to the peers but not collected yet
+  unsigned long long rr_seq;
+  unsigned int counter, counter2;
   PeerComm* peer;   // non-null: reductions are all-reduced inside the kernel over peer memory
 };
 
@@ -200,48 +202,117 @@ __device__ __forceinline__ void block_partials_finish(const double (&v)[NS], dou
   if (st->world > 1 && pc != nullptr && which != FIN_NONE && which != FIN_PLAIN) {
     // one-shot allreduce over peer memory: every rank stores its partial sums into every rank's
     // slot array, then waits for all contributions and adds them in rank order (bitwise identical
-    // on all ranks).  Parity double-buffering: a rank can be at most one reduction ahead.
+    // on all ranks).  Slots are four-deep in the sequence number.
+    // Single-pass recurrence: the r.r of the fused vector pass (FIN_RR2) is only POSTED here; it is
+    // collected together with p.Ap / Ap.Ap in the next K.u kernel (FIN_PAP2) or by k_cg_flush, so an
+    // iteration has ONE rendezvous instead of two and the r.r transfer overlaps the next K.u.
     __shared__ double sh_sums[NS];
     __shared__ double sh_recv[kMaxRanks][NS];
+    __shared__ double sh_rr[kMaxRanks];
     const unsigned long long seq = pc->seq + 1;
-    const int par = (int)(seq & 1);
+    const int par = (int)(seq & 3);
+    const bool defer = which == FIN_RR2;
+    const bool collect_rr = which == FIN_PAP2 && st->rr_pending != 0;
+    const unsigned long long rr_seq = st->rr_seq;
     if (threadIdx.x == 0) {
 #pragma unroll
       for (int k = 0; k < NS; ++k) sh_sums[k] = a[k];
     }
     __syncthreads();
     const double tag = __longlong_as_double((long long)seq);
-    if ((int)threadIdx.x < pc->world * NS) {
+    const int nposts = pc->world * NS;
+    if ((int)threadIdx.x < nposts) {
       // thread (r, k): store scalar k into rank r's slot, then poll rank r's scalar k in my slots
       const int r = threadIdx.x / NS, k = threadIdx.x % NS;
-      double2* dst = &pc->block[r]->slots[par][pc->rank][k];
+      double2* dst = &pc->block[r]->slots[par][pc->rank][defer ? 4 + k : k];
       asm volatile("st.volatile.global.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(sh_sums[k]), "d"(tag) : "memory");
-      const double2* src = &pc->block[pc->rank]->slots[par][r][k];
+      if (!defer) {
+        const double2* src = &pc->block[pc->rank]->slots[par][r][k];
+        double val, got;
+        long long spins = 0;
+        while (true) {
+          asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(val), "=d"(got) : "l"(src) : "memory");
+          if (__double_as_longlong(got) == (long long)seq) break;
+          if (++spins > kSpinLimit) {
+            pc->timeout = 1;
+            val = 0.0;
+            break;
+          }
+        }
+        sh_recv[r][k] = val;
+      }
+    } else if (collect_rr && (int)threadIdx.x < nposts + pc->world) {
+      const int r = threadIdx.x - nposts;
+      const double2* src = &pc->block[pc->rank]->slots[(int)(rr_seq & 3)][r][4];
       double val, got;
       long long spins = 0;
       while (true) {
         asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(val), "=d"(got) : "l"(src) : "memory");
-        if (__double_as_longlong(got) == (long long)seq) break;
+        if (__double_as_longlong(got) == (long long)rr_seq) break;
         if (++spins > kSpinLimit) {
           pc->timeout = 1;
           val = 0.0;
           break;
         }
       }
-      sh_recv[r][k] = val;
+      sh_rr[r] = val;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-#pragma unroll
-      for (int k = 0; k < NS; ++k) {
-        double g = 0.0;
-        for (int r = 0; r < pc->world; ++r) g += sh_recv[r][k];  // rank order: identical on all ranks
-        st->gsums[k] = g;
-      }
       pc->seq = seq;
-      if (pc->timeout) st->nonfinite = 2;
-      cg_finalize(st, which);
+      if (defer) {
+        st->rr_seq = seq;
+        st->rr_pending = 1;
+      } else {
+        if (collect_rr) {
+          double g = 0.0;
+          for (int r = 0; r < pc->world; ++r) g += sh_rr[r];
+          st->gsums[0] = g;
+          st->rr_pending = 0;
+          cg_finalize(st, FIN_RR2);
+        }
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+          double g = 0.0;
+          for (int r = 0; r < pc->world; ++r) g += sh_recv[r][k];  // rank order: identical on all ranks
+          st->gsums[k] = g;
+        }
+        if (pc->timeout) st->nonfinite = 2;
+        if (!(collect_rr && st->done)) cg_finalize(st, which);
+      }
     }
+  }
+}
+
+// collects a posted-but-pending r.r (see block_partials_finish): run after the last iteration of a batch
+__global__ void k_cg_flush(CGState* st) {
+  __shared__ double sh_rr[kMaxRanks];
+  PeerComm* pc = st->peer;
+  if (pc == nullptr || !st->rr_pending) return;
+  const unsigned long long rr_seq = st->rr_seq;
+  if ((int)threadIdx.x < pc->world) {
+    const double2* src = &pc->block[pc->rank]->slots[(int)(rr_seq & 3)][threadIdx.x][4];
+    double val, got;
+    long long spins = 0;
+    while (true) {
+      asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(val), "=d"(got) : "l"(src) : "memory");
+      if (__double_as_longlong(got) == (long long)rr_seq) break;
+      if (++spins > kSpinLimit) {
+        pc->timeout = 1;
+        val = 0.0;
+        break;
+      }
+    }
+    sh_rr[threadIdx.x] = val;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double g = 0.0;
+    for (int r = 0; r < pc->world; ++r) g += sh_rr[r];
+    st->gsums[0] = g;
+    st->rr_pending = 0;
+    if (pc->timeout) st->nonfinite = 2;
+    cg_finalize(st, FIN_RR2);
   }
 }
 
@@ -613,13 +684,13 @@ __global__ void __launch_bounds__(kBlock) k_update_xr(long long off, long long n
 __global__ void __launch_bounds__(kBlock) k_update_xrp(long long off, long long n, double* __restrict__ x,
                                                        double* __restrict__ r, double* __restrict__ p,
                                                        const double* __restrict__ Ap, double* partials, CGState* st,
-                                                       int signal_halo) {
+                                                       long long halo_n) {
   __shared__ double sm[32];
   if (st->done) return;
   const double alpha = st->alpha, beta = st->beta;
   double v[1] = {0.0};
   const long long stride = (long long)gridDim.x * blockDim.x;
-  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   x += off;
   r += off;
   p += off;
@@ -631,20 +702,39 @@ __global__ void __launch_bounds__(kBlock) k_update_xrp(long long off, long long 
     p[k] = fma(beta, pk, rv);
     v[0] = fma(rv, rv, v[0]);
   };
-  for (; t + 3 * stride < n; t += 4 * stride) {
-    double xk[4], rk[4], pk[4], ak[4];
+  auto range = [&](long long lo, long long hi) {
+    long long t = lo + t0;
+    for (; t + 3 * stride < hi; t += 4 * stride) {
+      double xk[4], rk[4], pk[4], ak[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      xk[k] = x[t + k * stride];
-      rk[k] = r[t + k * stride];
-      pk[k] = p[t + k * stride];
-      ak[k] = Ap[t + k * stride];
+      for (int k = 0; k < 4; ++k) {
+        xk[k] = x[t + k * stride];
+        rk[k] = r[t + k * stride];
+        pk[k] = p[t + k * stride];
+        ak[k] = Ap[t + k * stride];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) body(t + k * stride, xk[k], rk[k], pk[k], ak[k]);
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) body(t + k * stride, xk[k], rk[k], pk[k], ak[k]);
+    for (; t < hi; t += stride) body(t, x[t], r[t], p[t], Ap[t]);
+  };
+  if (halo_n > 0 && 2 * halo_n < n) {
+    // multi-GPU: the two boundary planes first; the last block to finish them tells the slab neighbours that this
+    // rank's direction vector is final there, long before their next K.u kernel asks for it
+    range(0, halo_n);
+    range(n - halo_n, n);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int tk = atomicInc(&st->counter2, gridDim.x - 1);
+      if (tk == gridDim.x - 1) signal_halo_flags(st);
+    }
+    range(halo_n, n - halo_n);
+    block_partials_finish<1>(v, partials, st, FIN_RR2, sm, false);
+  } else {
+    range(0, n);
+    block_partials_finish<1>(v, partials, st, FIN_RR2, sm, halo_n > 0);
   }
-  for (; t < n; t += stride) body(t, x[t], r[t], p[t], Ap[t]);
-  block_partials_finish<1>(v, partials, st, FIN_RR2, sm, signal_halo != 0);
 }
 
 // plain dot over owned dofs -> st->sums[0]

@@ -283,10 +283,12 @@ class GenericFEASolver:
         return ms.value
 
 
-def getcompliance(solver):
-    """FEA.getcompliance (src/FEA/FEA.jl:40): u'Ku = dot(u, f) for the solved system."""
+def getcompliance(solver, u=None):
+    """FEA.getcompliance (src/FEA/FEA.jl:40): u' K u, evaluated on the device with the current stiffness
+    (``u`` None = the device-resident solution).  Equals dot(u, f) only for a fully converged default solve."""
     out = C.c_double()
-    solver._check(solver._lib.topopt_dot(solver.handle, None, None, C.byref(out)))
+    up = None if u is None else _lib.ptr(np.ascontiguousarray(u, dtype=np.float64))
+    solver._check(solver._lib.topopt_quadratic_form(solver.handle, up, C.byref(out)))
     return out.value
 
 

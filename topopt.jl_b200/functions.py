@@ -86,3 +86,57 @@ class VolumeFun:
 
     def value_and_grad(self, x):
         return self(x), self.grad.copy()
+
+
+class _FieldFun:
+    """Shared body of DisplacementFun / TemperatureFun: value = the solved field, pullback = one adjoint solve
+    with the cotangent as right-hand side and the bilinear element form."""
+
+    _physics = None
+
+    def __init__(self, solver, maxfevals=10**8):
+        if self._physics is not None and getattr(solver.problem, "physics", self._physics) != self._physics:
+            kind = "StiffnessTopOptProblem" if self._physics == _lib.PHYSICS_ELASTICITY else "HeatTransferTopOptProblem"
+            raise ValueError(f"{type(self).__name__} can only be used with {kind}")  # ArgumentError in the reference
+        self.solver = solver
+        self.problem = solver.problem
+        self.u = np.zeros(solver.problem.ndof)
+        self.dudx_tmp = np.zeros(solver.problem.nel)
+        self.fevals = 0
+        self.maxfevals = maxfevals
+
+    def __call__(self, x):
+        """solver.vars .= x; solver(); copy(solver.u)  (displacement.jl:70-84, temperature.jl:71-83)"""
+        s = self.solver
+        self.fevals += 1
+        s.vars = _x(x)
+        s(download=True)
+        self.u = s.u.copy()
+        return self.u.copy()
+
+    def pullback(self, delta):
+        """(du/dx)' delta: K lam = delta (apply_zero! on the rhs, solvers_api.jl:364-367), then
+        out_e = -dE_e u_e' Ke lam_e  (displacement.jl:97-121, temperature.jl:92-119).  Both fields vanish on
+        the prescribed dofs (homogeneous Dirichlet), so bcmatrix(Ke) and rawmatrix(Ke) give the same form."""
+        s = self.solver
+        lam = s(assemble_f=False, rhs=np.ascontiguousarray(delta, dtype=np.float64), lhs=np.zeros(self.problem.ndof))
+        # device: resident solution = lam -> move it to the lambda slot, upload the forward field as u
+        s._check(s._lib.topopt_swap_solution_lambda(s.handle))
+        s._check(s._lib.topopt_bilinear_sens(s.handle, None, _lib.ptr(self.u), None, _lib.ptr(self.dudx_tmp)))
+        self.lam = lam
+        return -self.dudx_tmp
+
+    def value_and_pullback(self, x):
+        return self(x), self.pullback
+
+
+class DisplacementFun(_FieldFun):
+    """src/Functions/displacement.jl:28-121"""
+
+    _physics = _lib.PHYSICS_ELASTICITY
+
+
+class TemperatureFun(_FieldFun):
+    """src/Functions/temperature.jl:30-119"""
+
+    _physics = _lib.PHYSICS_HEAT
