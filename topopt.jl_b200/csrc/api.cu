@@ -79,9 +79,11 @@ struct topopt_handle {
   double Ke[kMaxKe * kMaxKe];
   double Kh[48];          // modal coefficients (hex8 elasticity fast path)
   bool modal_ok = false;  // Ke has the brick/isotropic modal sparsity pattern
+  bool modal_cube = false;  // ... and the 8-value structure of cubic cells (kxu_hex8_ring.cuh: cKc)
+  double Kc[8] = {0};
   int kxu_ty = 16, kxu_waves = 1, kxu_nsync = 1, kxu_2row = 1;  // 2row: 0 = one-row kernel, 1 = auto, else thread rows
   int kxu_ring = 1;       // ring-staged kernel for premasked inputs (CG directions): 0 = off, 1 = auto, else thread rows
-  int kxu_stagger = 0;    // ring kernel: stagger the thread rows at segment starts
+  int kxu_cube = 1;       // ring kernel: use the cubic-cell specialisation of the modal matrix when it applies
   int kxu_ring_min = 12;  // fewest owned node planes per rank for which the ring kernel is selected
   int cg_variant_env = -1;  // TOPOPT_CG_VARIANT overrides topopt_cg_opts.variant (diagnostics)
   double fixed_diag = 0.0, cellvol = 1.0;
@@ -221,6 +223,7 @@ int use_device(topopt_handle* h) {
     CUDA_TRY(h, cudaDeviceSynchronize());
     CUDA_TRY(h, cudaMemcpyToSymbol(cKe, h->Ke, sizeof(double) * h->ks * h->ks, 0, cudaMemcpyHostToDevice));
     if (h->modal_ok) CUDA_TRY(h, cudaMemcpyToSymbol(cKh, h->Kh, sizeof(double) * 48, 0, cudaMemcpyHostToDevice));
+    if (h->modal_cube) CUDA_TRY(h, cudaMemcpyToSymbol(cKc, h->Kc, sizeof(double) * 8, 0, cudaMemcpyHostToDevice));
     g_const_owner[h->device & 63] = h->id;
   }
   return TOPOPT_OK;
@@ -391,7 +394,7 @@ int launch_hex8_ring_t(topopt_handle* h, const double* x, double* y, int fin) {
     if (h->peer_p_lo) xlo = h->peer_p_lo + (size_t)h->plane_dofs * h->nown_lower;
     if (h->peer_p_hi) xhi = h->peer_p_hi + (size_t)h->plane_dofs;
   }
-  if (h->kxu_stagger) {
+  if (h->modal_cube && h->kxu_cube) {
     static std::atomic<unsigned long long> attr_mask{0};
     TRY(ensure_dyn_smem(h, k_apply_hex8_ring<TYT, NST, DOT, PEER, true>, smem, attr_mask));
     k_apply_hex8_ring<TYT, NST, DOT, PEER, true><<<grid, 32 * (TYT + 1), smem, h->stream>>>(g, x, y, h->d_E, h->d_fixed, h->fixed_diag, tilesX, tilesY,
@@ -1028,6 +1031,26 @@ int topopt_create(const topopt_desc* d, topopt_handle** out) {
     for (int k = 0; k < 24 * 24 && ok; ++k)
       if (!in_pattern[k] && std::fabs(Kh[k]) > 1e-11 * kmax) ok = false;
     h->modal_ok = ok;
+    if (ok) {
+      // cubic cells: [a b b; ...] normal block, c [1 1; 1 1] shear pairs, [p q; q p] bilinear pairs, [e f f; ...] triple, g
+      const double* K = h->Kh;
+      auto eq = [&](double u, double v) { return std::fabs(u - v) <= 1e-13 * kmax; };
+      bool cube = eq(K[0], K[4]) && eq(K[0], K[8]);
+      for (int k : {1, 2, 3, 5, 6, 7}) cube = cube && eq(K[k], K[1]);
+      for (int k = 9; k < 21; ++k) cube = cube && eq(K[k], K[9]);
+      for (int blk = 0; blk < 3; ++blk) {
+        const double* B = K + 21 + 4 * blk;
+        cube = cube && eq(B[0], K[21]) && eq(B[3], K[21]) && eq(B[1], K[22]) && eq(B[2], K[22]);
+      }
+      cube = cube && eq(K[33], K[37]) && eq(K[33], K[41]);
+      for (int k : {34, 35, 36, 38, 39, 40}) cube = cube && eq(K[k], K[34]);
+      cube = cube && eq(K[42], K[43]) && eq(K[42], K[44]);
+      h->modal_cube = cube;
+      if (cube) {
+        const double v[8] = {K[0] - K[1], K[1], K[9], K[21], K[22], K[33] - K[34], K[34], K[42]};
+        std::memcpy(h->Kc, v, sizeof(v));
+      }
+    }
     if (const char* e = getenv("TOPOPT_KXU_TY")) h->kxu_ty = atoi(e);
     if (getenv("TOPOPT_FUSE_P")) h->no_fuse = false;
     if (getenv("TOPOPT_NO_GRAPH")) h->use_graphs = false;
@@ -1036,7 +1059,7 @@ int topopt_create(const topopt_desc* d, topopt_handle** out) {
     if (const char* e = getenv("TOPOPT_KXU_2ROW")) h->kxu_2row = atoi(e);
     if (const char* e = getenv("TOPOPT_KXU_RING")) h->kxu_ring = atoi(e);
     if (const char* e = getenv("TOPOPT_KXU_RING_MIN")) h->kxu_ring_min = atoi(e);
-    if (const char* e = getenv("TOPOPT_KXU_STAGGER")) h->kxu_stagger = atoi(e);
+    if (const char* e = getenv("TOPOPT_KXU_CUBE")) h->kxu_cube = atoi(e);
   }
   if (const char* e = getenv("TOPOPT_CG_VARIANT")) h->cg_variant_env = atoi(e);
 

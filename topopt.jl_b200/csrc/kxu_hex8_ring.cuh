@@ -116,6 +116,66 @@ __device__ __forceinline__ void hex8_core(const RowX& L, const RowX& U, double (
   }
 }
 
+// Cubic cells (hx = hy = hz) with an isotropic material: the 45 modal coefficients collapse to 8 distinct values
+//   normal block  [a b b; b a b; b b a]      shear pairs  c [1 1; 1 1]      bilinear pairs  [p q; q p]
+//   bilinear triple  [e f f; f e f; f f e]   trilinear diagonal  g
+// (verified numerically at topopt_create).  cKc = {a - b, b, c, p, q, e - f, f, g}: 30 instead of 42 fp64 instructions
+// for the modal product and few enough constants to stay in uniform registers for the whole kernel.
+__constant__ double cKc[8];
+
+template <bool CUBE>
+__device__ __forceinline__ void hex8_core_t(const RowX& L, const RowX& U, double (&wL)[2][2][3], double (&wU)[2][2][3]) {
+  if (!CUBE) {
+    hex8_core(L, U, wL, wU);
+    return;
+  }
+  double X[3], Y[3], Z[3], XY[3], YZ[3], XZ[3], XYZ[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    X[c] = U.ds[c] + L.ds[c];
+    Y[c] = U.ss[c] - L.ss[c];
+    Z[c] = U.sd[c] + L.sd[c];
+    XY[c] = U.ds[c] - L.ds[c];
+    YZ[c] = U.sd[c] - L.sd[c];
+    XZ[c] = U.dd[c] + L.dd[c];
+    XYZ[c] = U.dd[c] - L.dd[c];
+  }
+  const double amb = cKc[0], b = cKc[1], cs = cKc[2], pp = cKc[3], qq = cKc[4], emf = cKc[5], ff = cKc[6], gg = cKc[7];
+  double vX[3], vY[3], vZ[3], vXY[3], vYZ[3], vXZ[3];
+  {  // normal block on (X.x, Y.y, Z.z)
+    const double t = b * ((X[0] + Y[1]) + Z[2]);
+    vX[0] = fma(amb, X[0], t);
+    vY[1] = fma(amb, Y[1], t);
+    vZ[2] = fma(amb, Z[2], t);
+  }
+  vX[1] = vY[0] = cs * (X[1] + Y[0]);  // shear pairs {X.y, Y.x}, {X.z, Z.x}, {Y.z, Z.y}
+  vX[2] = vZ[0] = cs * (X[2] + Z[0]);
+  vY[2] = vZ[1] = cs * (Y[2] + Z[1]);
+  vXY[0] = fma(qq, YZ[2], pp * XY[0]);  // bilinear pairs {XY.x, YZ.z}, {XY.y, XZ.z}, {YZ.y, XZ.x}
+  vYZ[2] = fma(pp, YZ[2], qq * XY[0]);
+  vXY[1] = fma(qq, XZ[2], pp * XY[1]);
+  vXZ[2] = fma(pp, XZ[2], qq * XY[1]);
+  vYZ[1] = fma(qq, XZ[0], pp * YZ[1]);
+  vXZ[0] = fma(pp, XZ[0], qq * YZ[1]);
+  {  // bilinear triple on (XY.z, YZ.x, XZ.y)
+    const double t = ff * ((XY[2] + YZ[0]) + XZ[1]);
+    vXY[2] = fma(emf, XY[2], t);
+    vYZ[0] = fma(emf, YZ[0], t);
+    vXZ[1] = fma(emf, XZ[1], t);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    wU[0][0][c] = vY[c];
+    wL[0][0][c] = -vY[c];
+    wU[1][0][c] = vX[c] + vXY[c];
+    wL[1][0][c] = vX[c] - vXY[c];
+    wU[0][1][c] = vZ[c] + vYZ[c];
+    wL[0][1][c] = vZ[c] - vYZ[c];
+    wU[1][1][c] = fma(gg, XYZ[c], vXZ[c]);
+    wL[1][1][c] = fma(-gg, XYZ[c], vXZ[c]);
+  }
+}
+
 // One stage of a warp's private ring: node rows A, B, C of a plane (E_e and the prescribed-dof flags, 10 bytes per
 // thread and step, come through ordinary loads issued one step ahead).
 constexpr int kRingStage = 3 * kRingPitch;
@@ -141,7 +201,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Warp-specialised: TYT compute warps (thread rows) + ONE producer warp that issues every bulk copy of the
 // CTA (the TMA producer / consumer pipeline: full[w][s] = data landed, empty[w][s] = stage released).
 // DOT: 0 = none, 1 = sum x.y, 2 = sum x.y and sum y.y (single-pass CG)
-template <int TYT, int NST, int DOT, bool PEER, bool STAGGER>
+template <int TYT, int NST, int DOT, bool PEER, bool CUBE>
 __global__ void __launch_bounds__(32 * (TYT + 1), (TYT <= 5 ? 2 : 1))
     k_apply_hex8_ring(Geo g, const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ E,
                       const unsigned char* __restrict__ fixed, double fixed_diag, int tilesX, int tilesY, double* partials,
@@ -153,7 +213,8 @@ __global__ void __launch_bounds__(32 * (TYT + 1), (TYT <= 5 ? 2 : 1))
   // y exchange: [step % 3][value][thread row + 1][lane]; row 0 stays zero (the bottom thread row has no lower neighbour)
   double(*yb)[6][TYT + 1][32] = reinterpret_cast<double(*)[6][TYT + 1][32]>(smem_raw + TYT * WRING);
   __shared__ uint64_t full[TYT][NST], empty[TYT][NST];
-  __shared__ int sflag[TYT], sstart[TYT];
+  __shared__ int sflag[TYT];
+  __shared__ double zero3[4];  // what non-owned lanes read as their x: keeps the tail branch-free
   __shared__ double sm[32];
   if (DOT && st->done) return;
   const int tid = threadIdx.x;
@@ -168,7 +229,8 @@ __global__ void __launch_bounds__(32 * (TYT + 1), (TYT <= 5 ? 2 : 1))
     mbar_init(&empty[tid / NST][tid % NST], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < TYT) sflag[tid] = sstart[tid] = 0;
+  if (tid < TYT) sflag[tid] = 0;
+  if (tid < 4) zero3[tid] = 0.0;
   // stale ring contents are read for out-of-domain nodes (their elements get E = 0): keep them finite
   for (int i = tid; i < TYT * WRING / 16; i += 32 * (TYT + 1)) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < 3 * 6 * (TYT + 1) * 32; i += 32 * (TYT + 1)) (&yb[0][0][0][0])[i] = 0.0;
@@ -184,83 +246,106 @@ __global__ void __launch_bounds__(32 * (TYT + 1), (TYT <= 5 ? 2 : 1))
 
   if (producer) {
     // =========================== producer warp ===========================
-    unsigned fcount = 0;  // planes filled so far (every compute warp gets one fill per plane)
-    while (u0 < u1) {
-      const int tile = (int)(u0 / g.nown);
-      const int zoff = (int)(u0 % g.nown);
-      const int zlen = (int)min((long long)(g.nown - zoff), u1 - u0);
-      u0 += zlen;
-      const int bx = tile % tilesX, by = tile / tilesX;
-      const int c0 = bx * 31 - 1;
-      const int z0 = 1 + zoff, z1 = z0 + zlen, first = z0 - 1, last = z1;
-      const int c_lo = max(c0, 0), cnt = min(c0 + 33, g.NX) - c_lo;
-      const int shift = c_lo - c0;
-      if (PEER && (xlo != nullptr || xhi != nullptr)) {
-        // ghost planes are read from the slab neighbours' memory: wait for their "direction vector final" flag
-        const bool need_lo = xlo != nullptr && z0 == 1, need_hi = xhi != nullptr && z1 == g.nown + 1;
-        if ((need_lo || need_hi) && tx == 0) {
-          PeerComm* pc = st->peer;
-          const unsigned long long want = pc->halo_seq;
-          volatile unsigned long long* f = pc->block[pc->rank]->halo_flag;
-          long long spins = 0;
-          while ((need_lo && f[0] < want) || (need_hi && f[1] < want)) {
-            if (++spins > kSpinLimit) {
-              pc->timeout = 1;
-              break;
-            }
-          }
-          __threadfence_system();
-        }
-        __syncwarp();
-        asm volatile("fence.proxy.async;" ::: "memory");
-      }
-      // this lane's jobs: j = tx, tx + 32, ... -> (compute warp row w, node row k = A, B, C)
-      constexpr int NJ = kRingJobs * TYT, JPL = (NJ + 31) / 32;
-      long long jidx[JPL];
-      int jdst[JPL], jw[JPL];
-      bool jvalid[JPL], jok[JPL];
+    // Every lane is an independent state machine for one (compute warp, node row) job: it walks the same segment list
+    // as the compute warps and refills a ring stage as soon as THAT warp has released it, so the rows never wait for
+    // each other through the producer.
+    constexpr int NJ = kRingJobs * TYT, JPL = (NJ + 31) / 32;
+    struct Job {
+      long long su0;      // first unit of the next segment
+      long long idx;      // byte offset of the row inside a plane
+      int P, last;        // next plane to fill, last plane of the current segment
+      int dst, w, k;      // ring offset, compute warp, row
+      unsigned fcount;    // fills issued so far
+      uint32_t bytes;
+      bool valid, done, ok;
+    } job[JPL];
+#pragma unroll
+    for (int q = 0; q < JPL; ++q) {
+      const int j = tx + 32 * q;
+      job[q].valid = j < NJ;
+      job[q].done = !job[q].valid;
+      job[q].w = j / kRingJobs;
+      job[q].k = j % kRingJobs;
+      job[q].su0 = u0;
+      job[q].P = 1;
+      job[q].last = 0;  // "segment exhausted": the first pass sets up the first segment
+      job[q].fcount = 0;
+      job[q].idx = 0;
+      job[q].dst = 0;
+      job[q].bytes = 0;
+      job[q].ok = false;
+    }
+    long long halo_spins = 0;
+    bool alldone;
+    do {
+      bool progressed = false;
+      alldone = true;
 #pragma unroll
       for (int q = 0; q < JPL; ++q) {
-        const int j = tx + 32 * q;
-        const int w = j / kRingJobs, k = j % kRingJobs;
-        const int frow = by * OWNR - 1 + 2 * w + k;
-        jw[q] = w;
-        jvalid[q] = j < NJ;
-        jok[q] = j < NJ && frow >= 0 && frow < g.NY;
-        jidx[q] = 24ll * ((long long)frow * g.NX + c_lo);
-        jdst[q] = w * WRING + k * kRingPitch + (shift ? 32 : 0);
-      }
-      const uint32_t jbytes = 24u * (uint32_t)cnt;
-      for (int P = first; P <= last; ++P, ++fcount) {
-        const int s = (int)(fcount % NST);
-        const uint32_t rel_par = ((fcount / NST) + 1u) & 1u;  // parity of the release of the previous use of stage s
-        const char* pp = reinterpret_cast<const char*>(x + (long long)P * g.S * 3);
-        if (PEER) {
-          if (xlo != nullptr && P == 0) pp = reinterpret_cast<const char*>(xlo);
-          if (xhi != nullptr && P == g.nown + 1) pp = reinterpret_cast<const char*>(xhi);
+        Job& J = job[q];
+        if (J.done) continue;
+        if (J.P > J.last) {  // next segment
+          if (J.su0 >= u1) {
+            J.done = true;
+            continue;
+          }
+          const int tile = (int)(J.su0 / g.nown);
+          const int zoff = (int)(J.su0 % g.nown);
+          const int zlen = (int)min((long long)(g.nown - zoff), u1 - J.su0);
+          J.su0 += zlen;
+          const int bx = tile % tilesX, by = tile / tilesX;
+          const int c0 = bx * 31 - 1;
+          const int c_lo = max(c0, 0), cnt = min(c0 + 33, g.NX) - c_lo;
+          const int frow = by * OWNR - 1 + 2 * J.w + J.k;
+          J.P = zoff;  // planes zoff .. zoff + zlen + 1
+          J.last = zoff + zlen + 1;
+          J.ok = frow >= 0 && frow < g.NY;
+          J.idx = 24ll * ((long long)frow * g.NX + c_lo);
+          J.dst = J.w * WRING + J.k * kRingPitch + (c_lo != c0 ? 32 : 0);
+          J.bytes = 24u * (uint32_t)cnt;
         }
-#pragma unroll
-        for (int q = 0; q < JPL; ++q) {
-          if (jvalid[q]) {
-            const int w = jw[q];
-            if (fcount >= NST) {
-              while (!mbar_try_wait(&empty[w][s], rel_par)) {
+        alldone = false;
+        const int sidx = (int)(J.fcount % NST);
+        bool ready = J.fcount < NST || mbar_test_wait(&empty[J.w][sidx], ((J.fcount / NST) + 1u) & 1u);
+        const char* pp = reinterpret_cast<const char*>(x + (long long)J.P * g.S * 3);
+        if (PEER) {
+          // ghost planes come straight from the slab neighbours' memory, once their "direction vector final" flag is up
+          const bool glo = xlo != nullptr && J.P == 0, ghi = xhi != nullptr && J.P == g.nown + 1;
+          if (glo || ghi) {
+            PeerComm* pc = st->peer;
+            const volatile unsigned long long* f = pc->block[pc->rank]->halo_flag;
+            if (f[glo ? 0 : 1] < pc->halo_seq) {
+              if (++halo_spins > kSpinLimit / 8) {
+                pc->timeout = 1;  // a dead peer must not hang the GPU: proceed, the solve reports the error
+              } else {
+                ready = false;
               }
             }
-            uint64_t* bar = &full[w][s];
-            if (jok[q]) {
-              const char* a = pp + jidx[q];
-              const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(a) & 15);
-              const uint32_t nb = (lead + jbytes + 15u) & ~15u;
-              mbar_arrive_expect_tx(bar, nb);
-              bulk_g2s(smem_raw + jdst[q] + s * kRingStage, a - lead, nb, bar);
-            } else {
-              mbar_arrive(bar);
+            pp = reinterpret_cast<const char*>(glo ? xlo : xhi);
+            if (ready) {
+              __threadfence_system();
+              asm volatile("fence.proxy.async;" ::: "memory");
             }
           }
         }
+        if (ready) {
+          uint64_t* bar = &full[J.w][sidx];
+          if (J.ok) {
+            const char* a = pp + J.idx;
+            const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(a) & 15);
+            const uint32_t nb = (lead + J.bytes + 15u) & ~15u;
+            mbar_arrive_expect_tx(bar, nb);
+            bulk_g2s(smem_raw + J.dst + sidx * kRingStage, a - lead, nb, bar);
+          } else {
+            mbar_arrive(bar);
+          }
+          J.P += 1;
+          J.fcount += 1;
+          progressed = true;
+        }
       }
-    }
+      if (!__any_sync(FULL, progressed)) __nanosleep(100);
+    } while (!__all_sync(FULL, alldone));
   } else {
     // =========================== compute warps ===========================
     unsigned char* ring = smem_raw + ty * WRING;  // this warp's ring
@@ -281,22 +366,9 @@ __global__ void __launch_bounds__(32 * (TYT + 1), (TYT <= 5 ? 2 : 1))
       const int c_lo = max(c0, 0);
       const int shift = c_lo - c0;  // 1 on the left-edge tile (column -1 does not exist)
       asm volatile("bar.sync 1, %0;" ::"n"(32 * TYT) : "memory");  // compute warps only: the previous segment's yb reads are complete
-      // Stagger the thread rows: a row starts a segment only after the row below has finished the forward
-      // stage of its first step.  All warps run the same code at the same pace, so without this the fp64-bound
-      // and the latency-bound parts of a step coincide on all warps of an SM sub-partition; the skew persists
-      // (a row never waits while it lags) and costs (TYT-1) x 1/6 step per ~50-step segment.
-      ++seg;
-      if (STAGGER && ty > 0) {
-        int spins = 0;
-        bool ready;
-        do {
-          ready = *(volatile int*)&sstart[ty - 1] >= seg || ++spins > (1 << 24);
-        } while (!__all_sync(FULL, ready));
-      }
 
       const int col = c0 + tx;
-      // byte offsets of this lane's slot inside a node / E / flag row (before the alignment lead)
-      const int lane_off = (shift ? 32 - 24 : 0) + 24 * tx;
+      const int lane_off = (shift ? 32 - 24 : 0) + 24 * tx;  // byte offset of this lane's node inside a ring row (before the lead)
       bool node_ok[2], own[2], el_ok[2];
       int ncol[2], ecol[2];
 #pragma unroll
@@ -337,20 +409,7 @@ __global__ void __launch_bounds__(32 * (TYT + 1), (TYT <= 5 ? 2 : 1))
         __syncwarp();
         if (tx == 0) mbar_arrive(&empty[ty][s]);
       };
-      // x stage of rows A, B, C of the plane held in stage s: a = x+1 + own, e = x+1 - own
-      auto xstage = [&](int s, unsigned pl, double (&a)[3][3], double (&e)[3][3]) {
-        const unsigned char* base = ring + s * kRingStage + lane_off;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const double* q = reinterpret_cast<const double*>(base + k * kRingPitch + (int)(pl ^ (k == 1 ? leadNB : leadN0)));
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const double o = q[c], r = q[3 + c];
-            a[k][c] = r + o;
-            e[k][c] = r - o;
-          }
-        }
-      };
+      auto prefetch_l1 = [](const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); };
 
       int s_tail = sf, s_old = sf, s_new = next_stage(sf);  // stages of planes ll - 1 (tail), ll, ll + 1 at step ll
       wait_stage(s_old, false);  // the first plane only serves as the bottom plane of the first layer
@@ -362,114 +421,124 @@ __global__ void __launch_bounds__(32 * (TYT + 1), (TYT <= 5 ? 2 : 1))
         for (int c = 0; c < 3; ++c) carry[r][c] = nA[r][c] = nB[r][c] = 0.0;
       double* yp[2] = {y + ((long long)(first - 1) * g.S + ncol[0]) * 3, y + ((long long)(first - 1) * g.S + ncol[1]) * 3};
       const long long ystep = (long long)g.S * 3;
-      // E_e of the layer and prescribed-dof flags of its bottom plane: plain loads, one step ahead
+      // E_e of the layer and the prescribed-dof flags of the plane being stored: 10 bytes per thread and step, pulled
+      // into L1 one step ahead (prefetch.global.L1 holds no register) and loaded where they are used
       const double* Ep[2] = {E + (long long)first * g.SE + ecol[0], E + (long long)first * g.SE + ecol[1]};
-      const unsigned char* fp[2] = {fixed + (long long)first * g.S + ncol[0], fixed + (long long)first * g.S + ncol[1]};
-      auto layer_ok = [&](int ll) -> bool {
-        const int gl = ll + g.p0;
-        return gl >= 0 && gl < g.NLg;
-      };
-      double En[2];
-      unsigned char flg[2] = {0, 0}, fln[2];
+      const unsigned char* fp[2] = {fixed + (long long)(first - 1) * g.S + ncol[0], fixed + (long long)(first - 1) * g.S + ncol[1]};
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        En[k] = (el_ok[k] && layer_ok(first)) ? Ep[k][0] : 0.0;
-        fln[k] = node_ok[k] ? fp[k][0] : 0;
-      }
-      int par = 0, hi_seen = 0;
+      for (int k = 0; k < 2; ++k)
+        if (el_ok[k]) prefetch_l1(Ep[k]);
+      int par = 0, hi_seen = 0, lo_seen = it;
 
-      // tail of step L: y reduction, inverse z stage, store of plane L, release of plane L's ring stage.
-      // It only depends on the thread row BELOW (its row C partial sums of step L), so the rows form a
-      // one-directional chain and settle into a staggered wavefront instead of meeting at every step.
-      // Called with L = first - 1 before the first step: a no-op (nothing stored, carry is overwritten by the
-      // next call before it is used).
-      auto tail = [&](int L, int parL) {
+      // Tail of layer L (deferred to the start of the next step): y reduction with the partial sums of the thread row
+      // below, inverse z stage, store of plane L, dot products, release of plane L's ring stage.  It only depends on the
+      // thread row BELOW, so the rows form a one-directional chain.  Branch-free: lanes that do not own their node
+      // read zeros as x and are treated as fully prescribed, so they store nothing and add 0 to the dot products.
+      // Called with L = first - 1 before the first step: a no-op (carry is overwritten before it is used).
+      auto tail = [&](int L, int parL, const unsigned char (&flraw)[2]) {
         {
           const int lo = ty > 0 ? ty - 1 : 0;
-          int spins = 0;
-          bool ready;
-          do {
-            ready = *(volatile int*)&sflag[lo] >= it || ++spins > (1 << 24);
-          } while (!__all_sync(FULL, ready));
+          if (!__all_sync(FULL, lo_seen >= it)) {  // lo_seen: read right after this row's own publication, a step ago
+            int spins = 0;
+            bool ready;
+            do {
+              ready = *(volatile int*)&sflag[lo] >= it || ++spins > (1 << 24);
+            } while (!__all_sync(FULL, ready));
+          }
           __threadfence_block();
+          // the row above must have consumed the y buffer this step will overwrite (written three steps ago):
+          // true once it has published step it - 2; read here, early, tested right before the stores
+          hi_seen = *(volatile int*)&sflag[ty + 1 < TYT ? ty + 1 : ty];
         }
-        // the row above must have consumed the y buffer this step will overwrite (written three steps ago):
-        // true once it has published step it - 2; read here, early, tested right before the stores
-        hi_seen = *(volatile int*)&sflag[ty + 1 < TYT ? ty + 1 : ty];
-        const bool store = L >= z0;
-        // raw x (prescribed rows, dot products) and flags of the plane being stored: still in the ring
-        const unsigned pl = plane_lead(L);
-        const unsigned char* sb = ring + s_tail * kRingStage;
+        double lowc[2][3], xo[2][3];
 #pragma unroll
         for (int m = 0; m < 2; ++m)
 #pragma unroll
-          for (int c = 0; c < 3; ++c) nA[m][c] += yb[parL][3 * m + c][ty][tx];
+          for (int c = 0; c < 3; ++c) lowc[m][c] = yb[parL][3 * m + c][ty][tx];
+        const bool store = L >= z0;
+        bool st_ok[2];
+        unsigned char fl[2];
+        {
+          const unsigned pl = plane_lead(L);
+          const unsigned char* sb = ring + s_tail * kRingStage + lane_off;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            st_ok[r] = store && own[r];
+            const double* q = st_ok[r] ? reinterpret_cast<const double*>(sb + r * kRingPitch + (int)(pl ^ (r == 1 ? leadNB : leadN0))) : zero3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) xo[r][c] = q[c];
+            fl[r] = st_ok[r] ? flraw[r] : (unsigned char)7;
+          }
+        }
+        if (L >= first) release_stage(s_tail);  // plane L has been read for the last time: hand its stage back
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) nA[m][c] += lowc[m][c];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           double(&n)[2][3] = r == 0 ? nA : nB;
-          const double* q = reinterpret_cast<const double*>(sb + lane_off + r * kRingPitch + (int)(pl ^ (r == 1 ? leadNB : leadN0)));
-          const unsigned char fl = flg[r];
-          const bool st_ok = store && own[r];
-          double xo[3], v[3];
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            xo[c] = q[c];
-            v[c] = carry[r][c] + (n[0][c] - n[1][c]);
+            double v = carry[r][c] + (n[0][c] - n[1][c]);
             carry[r][c] = n[0][c] + n[1][c];
-            if (fl & (1 << c)) v[c] = fixed_diag * xo[c];  // prescribed row: meandiag * x
-          }
-          if (st_ok) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              yp[r][c] = v[c];
-              if (DOT >= 1) dots[0] = fma(xo[c], v[c], dots[0]);
-              if (DOT == 2) dots[1] = fma(v[c], v[c], dots[1]);
-            }
+            if (fl[r] & (1 << c)) v = fixed_diag * xo[r][c];  // prescribed row: meandiag * x
+            if (st_ok[r]) yp[r][c] = v;
+            if (DOT >= 1) dots[0] = fma(xo[r][c], v, dots[0]);
+            if (DOT == 2) dots[1] = fma(v, v, dots[1]);
           }
           yp[r] += ystep;
         }
-        // plane L has been consumed by this warp (nobody else reads its ring): hand the stage back
-        if (L >= first) release_stage(s_tail);
       };
 
       for (int ll = first; ll < z1; ++ll, par = par == 2 ? 0 : par + 1) {  // element layer ll: planes ll (bottom), ll + 1 (top)
+        // E_e of this layer and the flags of the plane the tail stores: L1 hits (prefetched one step ago), issued
+        // before the waits so that their latency is hidden; then the prefetch for the next step
+        double Ee[2];
+        unsigned char flraw[2];
+        {
+          const int gl = ll + g.p0;
+          const bool lay = gl >= 0 && gl < g.NLg;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            Ee[k] = (el_ok[k] && lay) ? Ep[k][0] : 0.0;
+            flraw[k] = (node_ok[k] && ll - 1 >= z0) ? fp[k][0] : (unsigned char)0;
+            Ep[k] += g.SE;
+            fp[k] += g.S;
+            if (el_ok[k] && ll + 1 < z1) prefetch_l1(Ep[k]);
+            if (node_ok[k]) prefetch_l1(fp[k]);
+          }
+        }
         wait_stage(s_new, hint_new);
         hint_new = test_stage(next_stage(s_new));  // next step's plane: usually landed already
-        tail(ll - 1, par == 0 ? 2 : par - 1);
-        const double Ee[2] = {En[0], En[1]};
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          flg[k] = fln[k];  // flags of plane ll: used by tail(ll) one step later
-          Ep[k] += g.SE;
-          fp[k] += g.S;
-          En[k] = (el_ok[k] && ll + 1 < z1 && layer_ok(ll + 1)) ? Ep[k][0] : 0.0;
-          fln[k] = node_ok[k] ? fp[k][0] : 0;
-        }
+        tail(ll - 1, par == 0 ? 2 : par - 1, flraw);
         // ---- forward x and z stages of rows A, B, C from the raw planes ll and ll + 1
         RowX xr[3];
         {
-          double ab[3][3], eb[3][3], at[3][3], et[3][3];
-          xstage(s_old, plane_lead(ll), ab, eb);
-          xstage(s_new, plane_lead(ll + 1), at, et);
+          const unsigned plb = plane_lead(ll), plt = plane_lead(ll + 1);
+          const unsigned char* bb = ring + s_old * kRingStage + lane_off;
+          const unsigned char* bt = ring + s_new * kRingStage + lane_off;
 #pragma unroll
-          for (int k = 0; k < 3; ++k)
+          for (int k = 0; k < 3; ++k) {
+            const unsigned lk = k == 1 ? leadNB : leadN0;
+            const double* qb = reinterpret_cast<const double*>(bb + k * kRingPitch + (int)(plb ^ lk));
+            const double* qt = reinterpret_cast<const double*>(bt + k * kRingPitch + (int)(plt ^ lk));
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              xr[k].ss[c] = at[k][c] + ab[k][c];
-              xr[k].sd[c] = at[k][c] - ab[k][c];
-              xr[k].ds[c] = et[k][c] + eb[k][c];
-              xr[k].dd[c] = et[k][c] - eb[k][c];
+              const double ab = qb[3 + c] + qb[c], eb = qb[3 + c] - qb[c];
+              const double at = qt[3 + c] + qt[c], et = qt[3 + c] - qt[c];
+              xr[k].ss[c] = at + ab;
+              xr[k].sd[c] = at - ab;
+              xr[k].ds[c] = et + eb;
+              xr[k].dd[c] = et - eb;
             }
-        }
-        if (STAGGER && ll == first) {
-          __syncwarp();
-          if (tx == 0) *(volatile int*)&sstart[ty] = seg;
+          }
         }
         // ---- the two elements; E-scaled accumulation onto the x edges of rows A, B, C
         double WA[2][2][3], WB[2][2][3], WC[2][2][3];
         {
           double wL[2][2][3], wU[2][2][3];
-          hex8_core(xr[0], xr[1], wL, wU);
+          hex8_core_t<CUBE>(xr[0], xr[1], wL, wU);
 #pragma unroll
           for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -482,7 +551,7 @@ __global__ void __launch_bounds__(32 * (TYT + 1), (TYT <= 5 ? 2 : 1))
         }
         {
           double wL[2][2][3], wU[2][2][3];
-          hex8_core(xr[1], xr[2], wL, wU);
+          hex8_core_t<CUBE>(xr[1], xr[2], wL, wU);
 #pragma unroll
           for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -518,11 +587,17 @@ __global__ void __launch_bounds__(32 * (TYT + 1), (TYT <= 5 ? 2 : 1))
           __threadfence_block();
           *(volatile int*)&sflag[ty] = it;
         }
+        lo_seen = *(volatile int*)&sflag[ty > 0 ? ty - 1 : 0];  // consumed by the next tail
         s_tail = s_old;
         s_old = s_new;
         s_new = next_stage(s_new);
       }
-      tail(z1 - 1, par == 0 ? 2 : par - 1);
+      {
+        unsigned char flraw[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) flraw[k] = node_ok[k] ? fp[k][0] : (unsigned char)0;
+        tail(z1 - 1, par == 0 ? 2 : par - 1, flraw);
+      }
       release_stage(s_old);  // the top plane of the last layer was only read as a "new" plane
       sf = s_new;
     }  // segments
