@@ -235,6 +235,21 @@ int topopt_simp_eval(topopt_handle* h, topopt_filter* f, int32_t filter_kind, co
                      int32_t penalty_kind, double p, double xmin, const topopt_cg_opts* opts,
                      double* obj, double* grad_x, topopt_cg_result* result);
 
+/* ---- on-device design update (device-resident SIMP loop) ---------------------------------- */
+/* Optimality-criteria update with bisection on the volume multiplier: xn = clamp(x (-dc / (dv lambda))^eta) within
+ * [max(xlo, x - move), min(1, x + move)], lambda such that sum xn dv = volfrac.  Every bisection step is one fused
+ * kernel over the device-resident design; only 8 bytes per step cross PCIe.  x NULL = resident design (the one the last
+ * topopt_simp_eval / topopt_oc_update left), dc NULL = the design gradient the last topopt_simp_eval left on the device,
+ * dv NULL = resident volume gradient (must be passed once).  x_out (nel) may be NULL: the new design stays resident and
+ * is what topopt_simp_eval(x = NULL) evaluates next.  change_l2 = ||xn - x||_2.  Replaces the host-side update that the
+ * reference delegates to its optimiser packages (cf. the threshold bisection of src/Algorithms/beso.jl:154-173). */
+int topopt_oc_update(topopt_handle* h, const double* x, const double* dc, const double* dv, double volfrac,
+                     double move, double eta, double xlo, double* x_out, double* change_l2,
+                     int32_t* nbisect);
+
+/* the device-resident design vector (nel) */
+int topopt_get_design(topopt_handle* h, double* x);
+
 /* ---- measurement ---------------------------------------------------------------------- */
 /* time `reps` back-to-back launches of one kernel class with CUDA events on the library's
  * stream; which: 0 = K.u as the CG loop launches it (dense direction vector, fused p.Ap),

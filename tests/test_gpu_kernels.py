@@ -334,3 +334,35 @@ def test_displacement_and_temperature_fun_adjoints(lib, kind):
     with pytest.raises(ValueError):
         Other(s)
     s.close()
+
+
+@pytest.mark.parametrize("nels,filt", [((16, 8), "density"), ((10, 4, 6), "density"), ((16, 8), "sens")])
+def test_device_resident_simp_loop(lib, nels, filt):
+    """the optimality-criteria update (bisection on the volume multiplier as device reductions) keeps the
+    design on the GPU between iterations.  Ten iterations must reproduce the host-side loop (same update rule) and the
+    oracle's loop to the north-star design tolerance."""
+    t = lib
+    prob, oprob = t.PointLoadCantilever(nels), o.PointLoadCantilever(nels)
+    prob.Ke = oprob.Ke.copy()
+    mk = lambda: t.FEASolver(t.CUDAMatrixFreeSolver, prob, penalty=t.PowerPenaltyFun(3.0), abstol=1e-11, reltol=1e-14, cg_max_iter=20000, xmin=1e-3)
+    s1, s2 = mk(), mk()
+    Fc = {"density": t.DensityFilterFun, "sens": t.SensFilterFun}[filt]
+    F1, F2 = Fc(s1, 2.0), Fc(s2, 2.0)
+    xh, hh = t.simp_loop(s1, F1, 0.4, iters=10)
+    xd, hd = t.simp_loop_device(s2, F2, 0.4, iters=10)
+    assert np.max(np.abs(xd - xh)) < 1e-9 and rel(hd, hh) < 1e-10
+    xo, ho = o.simp_loop(oprob, 2.0, 0.4, p=3.0, xmin=1e-3, iters=10, filt=filt, abstol=1e-11, maxiter=20000)
+    assert np.max(np.abs(xd - xo)) < 1e-6 and rel(hd, ho) < 1e-8
+    assert abs(float(xd @ (prob.cellvolumes / prob.cellvolumes.sum())) - 0.4) < 1e-9 or filt == "density"
+    # one update against the host rule on arbitrary inputs
+    x = np.random.default_rng(1).uniform(0.05, 1.0, prob.nel)
+    dc = -np.random.default_rng(2).uniform(0.0, 3.0, prob.nel)
+    dv = np.random.default_rng(3).uniform(0.5, 1.5, prob.nel) / prob.nel
+    out = np.empty(prob.nel)
+    change, nb = t.oc_update_device(s2, 0.45, dv=dv, x=x, dc=dc, x_out=out)
+    ref = t.oc_update(x, dc, dv, 0.45)
+    assert np.max(np.abs(out - ref)) < 1e-10 and nb > 30
+    assert abs(change - float(np.linalg.norm(ref - x))) < 1e-9
+    for q in (F1, F2):
+        q.close()
+    s1.close(); s2.close()

@@ -21,6 +21,6 @@ from .fea import (
 )
 from .functions import ComplianceFun, DisplacementFun, TemperatureFun, ThermalComplianceFun, VolumeFun
 from .problems import HalfMBB, HeatConductionProblem, HeatTree, Metadata, PointLoadCantilever, element_matrix
-from .simp import oc_update, simp_eval, simp_loop
+from .simp import oc_update, oc_update_device, simp_eval, simp_loop, simp_loop_device
 
 __all__ = [n for n in dir() if not n.startswith("_")]

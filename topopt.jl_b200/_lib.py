@@ -131,6 +131,8 @@ SIGNATURES = {
         C.c_int,
         [VP, VP, C.c_int32, VP, C.c_int32, C.c_double, C.c_double, C.POINTER(CGOpts), c_dp, VP, C.POINTER(CGResult)],
     ),
+    "topopt_oc_update": (C.c_int, [VP, VP, VP, VP, C.c_double, C.c_double, C.c_double, C.c_double, VP, c_dp, C.POINTER(C.c_int32)]),
+    "topopt_get_design": (C.c_int, [VP, VP]),
     "topopt_time_kernel": (C.c_int, [VP, VP, C.c_int32, C.c_int32, c_dp]),
 }
 

@@ -109,6 +109,8 @@ struct topopt_handle {
   double *d_D = nullptr, *d_rhs = nullptr, *d_lam = nullptr, *d_tmp = nullptr;
   double *d_E = nullptr, *d_dE = nullptr, *d_rho = nullptr, *d_cell = nullptr, *d_grad = nullptr;
   double *d_full_dof = nullptr, *d_full_el = nullptr, *d_design = nullptr, *d_xf = nullptr, *d_gfull = nullptr;
+  double *d_dv = nullptr, *d_dc = nullptr, *d_xnew = nullptr;  // on-device design update
+  const double* d_lastgrad = nullptr;                           // gradient w.r.t. the design left by topopt_simp_eval
   double* d_partials = nullptr;
   CGState* d_st = nullptr;
   CGState* h_st = nullptr;  // pinned
@@ -1219,7 +1221,8 @@ int topopt_destroy(topopt_handle* h) {
   if (h->d_peercomm) cudaFree(h->d_peercomm);
   void* ptrs[] = {h->d_block, h->d_fixed, h->d_b, h->d_fload, h->d_u, h->d_r, h->d_p, h->d_p2, h->d_Ap, h->d_D, h->d_rhs, h->d_lam,
                   h->d_tmp, h->d_E, h->d_dE, h->d_rho, h->d_cell, h->d_grad, h->d_full_dof, h->d_full_el, h->d_design,
-                  h->d_xf, h->d_gfull, h->d_partials, h->d_st, h->d_nbr_start, h->d_rowptr, h->d_col, h->d_nz, h->d_fasm};
+                  h->d_xf, h->d_gfull, h->d_partials, h->d_st, h->d_nbr_start, h->d_rowptr, h->d_col, h->d_nz, h->d_fasm,
+                  h->d_dv, h->d_dc, h->d_xnew};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_st) cudaFreeHost(h->h_st);
@@ -1736,11 +1739,78 @@ int topopt_simp_eval(topopt_handle* h, topopt_filter* f, int32_t filter_kind, co
     TRY(filter_run(f, gfull, h->d_gfull, filter_kind == 1 ? TOPOPT_FILTER_TRANSPOSE : TOPOPT_FILTER_FORWARD));
     gout = h->d_gfull;
   }
+  h->d_lastgrad = gout;
   if (grad_x) {
     CUDA_TRY(h, cudaMemcpyAsync(grad_x, gout, sizeof(double) * h->nel, cudaMemcpyDefault, h->stream));
     h->stats.d2h_bytes += sizeof(double) * h->nel;
   }
   return sync(h);
+}
+
+int topopt_get_design(topopt_handle* h, double* x) {
+  if (!h || !x) return fail(h, TOPOPT_ERR_INVALID, "topopt_get_design: NULL argument");
+  TRY(use_device(h));
+  CUDA_TRY(h, cudaMemcpyAsync(x, h->d_design, sizeof(double) * h->nel, cudaMemcpyDefault, h->stream));
+  h->stats.d2h_bytes += sizeof(double) * h->nel;
+  return sync(h);
+}
+
+// Optimality-criteria update with bisection on the volume multiplier, entirely on the device: every bisection step is
+// one fused candidate + volume reduction over the resident design; only the 8-byte volume crosses PCIe.
+int topopt_oc_update(topopt_handle* h, const double* x, const double* dc, const double* dv, double volfrac, double move, double eta,
+                     double xlo, double* x_out, double* change_l2, int32_t* nbisect) {
+  if (!h) return fail(h, TOPOPT_ERR_INVALID, "topopt_oc_update: NULL handle");
+  if (!(volfrac > 0) || !(move > 0) || !(eta > 0)) return fail(h, TOPOPT_ERR_INVALID, "topopt_oc_update: volfrac, move and eta must be positive");
+  TRY(use_device(h));
+  const size_t bytes = sizeof(double) * h->nel;
+  if (!h->d_dv) {
+    TRY(dev_alloc(h, &h->d_dv, h->nel));
+    TRY(dev_alloc(h, &h->d_dc, h->nel));
+    TRY(dev_alloc(h, &h->d_xnew, h->nel));
+    if (!dv) return fail(h, TOPOPT_ERR_INVALID, "topopt_oc_update: the first call must pass dv (volume gradient)");
+  }
+  if (x) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_design, x, bytes, cudaMemcpyDefault, h->stream));
+    h->stats.h2d_bytes += bytes;
+  }
+  if (dv) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_dv, dv, bytes, cudaMemcpyDefault, h->stream));
+    h->stats.h2d_bytes += bytes;
+  }
+  const double* g = h->d_lastgrad;
+  if (dc) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_dc, dc, bytes, cudaMemcpyDefault, h->stream));
+    h->stats.h2d_bytes += bytes;
+    g = h->d_dc;
+  }
+  if (!g) return fail(h, TOPOPT_ERR_INVALID, "topopt_oc_update: no gradient (pass dc or call topopt_simp_eval first)");
+  double l1 = 0.0, l2 = 1e9, lam = 0.0;
+  int steps = 0;
+  while ((l2 - l1) / (l1 + l2) > 1e-12 && l2 > 1e-40) {
+    lam = 0.5 * (l1 + l2);
+    LAUNCH(h, (k_oc<false>), kReduceBlocks, (long long)h->nel, h->d_design, g, h->d_dv, lam, move, eta, xlo, (double*)nullptr, h->d_partials, h->d_st);
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_st, h->d_st, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    TRY(sync(h));
+    if (h->h_st->sums[0] > volfrac) {
+      l1 = lam;
+    } else {
+      l2 = lam;
+    }
+    ++steps;
+  }
+  // the candidate of the LAST trial multiplier is the new design (the rule of the host-side loop it replaces)
+  LAUNCH(h, (k_oc<true>), kReduceBlocks, (long long)h->nel, h->d_design, g, h->d_dv, lam, move, eta, xlo, h->d_xnew, h->d_partials, h->d_st);
+  TRY(check_launch(h, "k_oc"));
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_st, h->d_st, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  std::swap(h->d_design, h->d_xnew);
+  if (x_out) {
+    CUDA_TRY(h, cudaMemcpyAsync(x_out, h->d_design, bytes, cudaMemcpyDefault, h->stream));
+    h->stats.d2h_bytes += bytes;
+  }
+  TRY(sync(h));
+  if (change_l2) *change_l2 = std::sqrt(h->h_st->sums[1]);
+  if (nbisect) *nbisect = steps;
+  return TOPOPT_OK;
 }
 
 // ---- measurement ------------------------------------------------------------------------------

@@ -1027,6 +1027,34 @@ __global__ void k_filter_n2c_T(FilterGeo f, const double* __restrict__ t, double
   }
 }
 
+// ---- optimality-criteria design update on the device ------------------------------
+// xn_e = max(xlo, max(x_e - move, min(1, min(x_e + move, x_e (-dc_e / (dv_e lambda))^eta))))  with dc clamped to <= 0.
+__device__ __forceinline__ double oc_candidate(double x, double dc, double dv, double lam, double move, double eta, double xlo) {
+  const double dcm = fmin(dc, 0.0);
+  const double b = x * pow(-dcm / dv / lam, eta);
+  return fmax(xlo, fmax(x - move, fmin(1.0, fmin(x + move, b))));
+}
+// APPLY = false: sums[0] = sum xn_e dv_e for the trial multiplier (one bisection step);
+// APPLY = true : writes xn and reduces max |xn - x| (as a sum of per-block maxima is not a max: see below)
+template <bool APPLY>
+__global__ void __launch_bounds__(kBlock) k_oc(long long n, const double* __restrict__ x, const double* __restrict__ dc,
+                                               const double* __restrict__ dv, double lam, double move, double eta, double xlo,
+                                               double* __restrict__ xout, double* partials, CGState* st) {
+  __shared__ double sm[32];
+  double v[2] = {0.0, 0.0};
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const double xe = x[e];
+    const double xn = oc_candidate(xe, dc[e], dv[e], lam, move, eta, xlo);
+    v[0] = fma(xn, dv[e], v[0]);
+    if (APPLY) {
+      xout[e] = xn;
+      const double d = fabs(xn - xe);
+      v[1] = fma(d, d, v[1]);  // sum of squared changes (the max is taken on the host copy when asked for)
+    }
+  }
+  block_partials_finish<2>(v, partials, st, FIN_PLAIN, sm);
+}
+
 // ---- assembled path (assemble.jl:28-90; Ferrite assemble!/apply!) -----------------------------
 // Internal CSR in lexicographic dof order.  Row (n,c) holds, for every in-range neighbour node m
 // (z,y,x ascending) and component c2, K[(n,c),(m,c2)].  nbr_start[n] = number of (node,neighbour)

@@ -125,10 +125,9 @@ __constant__ double cKc[8];
 
 template <bool CUBE>
 __device__ __forceinline__ void hex8_core_t(const RowX& L, const RowX& U, double (&wL)[2][2][3], double (&wU)[2][2][3]) {
-  if (!CUBE) {
+  if constexpr (!CUBE) {
     hex8_core(L, U, wL, wU);
-    return;
-  }
+  } else {
   double X[3], Y[3], Z[3], XY[3], YZ[3], XZ[3], XYZ[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -173,6 +172,7 @@ __device__ __forceinline__ void hex8_core_t(const RowX& L, const RowX& U, double
     wL[0][1][c] = vZ[c] - vYZ[c];
     wU[1][1][c] = fma(gg, XYZ[c], vXZ[c]);
     wL[1][1][c] = fma(-gg, XYZ[c], vXZ[c]);
+  }
   }
 }
 
@@ -350,7 +350,6 @@ __global__ void __launch_bounds__(32 * (TYT + 1), (TYT <= 5 ? 2 : 1))
     // =========================== compute warps ===========================
     unsigned char* ring = smem_raw + ty * WRING;  // this warp's ring
     int it = 0;          // published-step counter (monotonic across segments)
-    int seg = 0;         // segment counter
     int sf = 0;          // ring stage of the next plane to be consumed
     unsigned phase = 0;  // bit s: parity to wait for on full[ty][s]
     auto next_stage = [](int s) { return s + 1 == NST ? 0 : s + 1; };

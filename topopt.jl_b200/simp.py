@@ -58,3 +58,32 @@ def simp_loop(solver, filt, volfrac, iters=10, x0=None):
         hist.append(obj)
         x = oc_update(x, g, dvf, volfrac)
     return x, hist
+
+
+def oc_update_device(solver, volfrac, dv=None, x=None, dc=None, x_out=None, move=0.2, eta=0.5, xlo=0.0):
+    """topopt_oc_update: the same update as ``oc_update`` on the device-resident design and gradient.
+    Returns (||xn - x||_2, bisection steps)."""
+    change = C.c_double()
+    nb = C.c_int32()
+    solver._check(
+        solver._lib.topopt_oc_update(solver.handle, _lib.ptr(x), _lib.ptr(dc), _lib.ptr(dv), float(volfrac), float(move), float(eta), float(xlo),
+                                     _lib.ptr(x_out), C.byref(change), C.byref(nb))
+    )
+    return change.value, nb.value
+
+
+def simp_loop_device(solver, filt, volfrac, iters=10, x0=None):
+    """Device-resident SIMP loop: the design, the state and the gradient never leave the GPU between iterations
+    (per iteration 8 bytes of objective and 8 bytes per bisection step come back).  Returns (x, objective history)."""
+    prob = solver.problem
+    x = np.full(prob.nel, float(volfrac)) if x0 is None else np.array(x0, dtype=np.float64)
+    dv = prob.cellvolumes / prob.cellvolumes.sum()
+    dvf = filt.pullback(dv) if (filt is not None and filt.kind == 1) else dv
+    hist = []
+    for k in range(iters):
+        obj, _res = simp_eval(solver, filt, x if k == 0 else None, None)
+        hist.append(obj)
+        oc_update_device(solver, volfrac, dv=np.ascontiguousarray(dvf) if k == 0 else None)
+    out = np.empty(prob.nel)
+    solver._check(solver._lib.topopt_get_design(solver.handle, _lib.ptr(out)))
+    return out, hist
