@@ -20,6 +20,7 @@
 #include "kxu_hex8.cuh"
 #include "kxu_hex8_2row.cuh"
 #include "kxu_hex8_ring.cuh"
+#include "multigrid.cuh"
 
 using namespace topopt;
 
@@ -62,6 +63,24 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 }  // namespace
+
+// one level of the geometric multigrid hierarchy (multigrid.cuh); level 0 aliases the handle's own grid
+struct MGLevel {
+  Geo g{};
+  int64_t nloc_nodes = 0, nloc_dofs = 0, off = 0, nown_dofs = 0, nloc_el = 0;
+  double *E = nullptr, *D = nullptr, *x = nullptr, *b = nullptr, *r = nullptr, *d = nullptr, *t = nullptr;
+  unsigned char* fixed = nullptr;
+  double lmax = 2.0;  // estimate of lambda_max(D^-1 K)
+  bool owns = false;  // E / fixed / b allocated by the hierarchy (levels >= 1)
+};
+struct MGHierarchy {
+  std::vector<MGLevel> lv;
+  double* d_Ainv = nullptr;  // dense inverse of the coarsest operator
+  int* d_loc = nullptr;      // dense dof -> local vector index on the coarsest level
+  int ncoarse = 0;
+  int degree = 2;            // Chebyshev smoother degree
+  long long cycles = 0;
+};
 
 struct topopt_handle {
   uint64_t id = 0;
@@ -111,6 +130,9 @@ struct topopt_handle {
   double *d_full_dof = nullptr, *d_full_el = nullptr, *d_design = nullptr, *d_xf = nullptr, *d_gfull = nullptr;
   double *d_dv = nullptr, *d_dc = nullptr, *d_xnew = nullptr;  // on-device design update
   const double* d_lastgrad = nullptr;                           // gradient w.r.t. the design left by topopt_simp_eval
+  MGHierarchy* mg = nullptr;   // geometric multigrid preconditioner (opt-in)
+  bool mg_dirty = true;        // coarse operators / smoother bounds must be rebuilt (stiffness changed)
+  const MGLevel* lvl = nullptr;  // K.u launchers act on this level instead of the handle's grid
   double* d_partials = nullptr;
   CGState* d_st = nullptr;
   CGState* h_st = nullptr;  // pinned
@@ -321,6 +343,10 @@ int sync(topopt_handle* h) {
 // ---- operator application -----------------------------------------------------------------
 constexpr int kMaxPartialBlocks = 16384;
 
+inline const Geo& cur_geo(const topopt_handle* h) { return h->lvl ? h->lvl->g : h->g; }
+inline const double* cur_E(const topopt_handle* h) { return h->lvl ? h->lvl->E : h->d_E; }
+inline const unsigned char* cur_fixed(const topopt_handle* h) { return h->lvl ? h->lvl->fixed : h->d_fixed; }
+
 // cudaFuncSetAttribute is per device: one bit per device ordinal for every kernel instantiation
 template <typename K>
 int ensure_dyn_smem(topopt_handle* h, K kernel, size_t smem, std::atomic<unsigned long long>& mask) {
@@ -333,7 +359,7 @@ int ensure_dyn_smem(topopt_handle* h, K kernel, size_t smem, std::atomic<unsigne
 
 template <int TY, bool DOT, bool FUSEP, bool PEER, bool NSYNC>
 int launch_hex8_modal(topopt_handle* h, const double* x, double* y, int fin, const double* r, double* pnew) {
-  const Geo& g = h->g;
+  const Geo& g = cur_geo(h);
   const int tilesX = (g.NX + 29) / 30, tilesY = (g.NY + TY - 3) / (TY - 2);
   // persistent grid: resident CTAs per SM (register-limited) x 148 SMs, capped by the work
   const int per_sm = TY <= 4 ? 4 : (TY <= 8 ? 2 : 1);
@@ -350,7 +376,7 @@ int launch_hex8_modal(topopt_handle* h, const double* x, double* y, int fin, con
     if (h->peer_p_lo) xlo = h->peer_p_lo + (size_t)h->plane_dofs * h->nown_lower;
     if (h->peer_p_hi) xhi = h->peer_p_hi + (size_t)h->plane_dofs;
   }
-  k_apply_hex8_modal<TY, DOT, FUSEP, PEER, NSYNC><<<grid, 32 * TY, smem, h->stream>>>(g, x, y, h->d_E, h->d_fixed, h->fixed_diag, tilesX,
+  k_apply_hex8_modal<TY, DOT, FUSEP, PEER, NSYNC><<<grid, 32 * TY, smem, h->stream>>>(g, x, y, cur_E(h), cur_fixed(h), h->fixed_diag, tilesX,
                                                                               tilesY, h->d_partials, h->d_st, fin, r, pnew, xlo, xhi);
   h->stats.kernel_launches += 1;
   return check_launch(h, "k_apply_hex8_modal");
@@ -358,7 +384,7 @@ int launch_hex8_modal(topopt_handle* h, const double* x, double* y, int fin, con
 
 template <int TYT, bool DOT, bool PEER>
 int launch_hex8_modal2(topopt_handle* h, const double* x, double* y, int fin) {
-  const Geo& g = h->g;
+  const Geo& g = cur_geo(h);
   constexpr int ROWS = 2 * TYT - 2;
   const int tilesX = (g.NX + 29) / 30, tilesY = (g.NY + ROWS - 1) / ROWS;
   int grid = 148 * std::max(1, h->kxu_waves);
@@ -373,7 +399,7 @@ int launch_hex8_modal2(topopt_handle* h, const double* x, double* y, int fin) {
     if (h->peer_p_lo) xlo = h->peer_p_lo + (size_t)h->plane_dofs * h->nown_lower;
     if (h->peer_p_hi) xhi = h->peer_p_hi + (size_t)h->plane_dofs;
   }
-  k_apply_hex8_modal2<TYT, DOT, PEER><<<grid, 32 * TYT, smem, h->stream>>>(g, x, y, h->d_E, h->d_fixed, h->fixed_diag, tilesX, tilesY,
+  k_apply_hex8_modal2<TYT, DOT, PEER><<<grid, 32 * TYT, smem, h->stream>>>(g, x, y, cur_E(h), cur_fixed(h), h->fixed_diag, tilesX, tilesY,
                                                                           h->d_partials, h->d_st, fin, xlo, xhi);
   h->stats.kernel_launches += 1;
   return check_launch(h, "k_apply_hex8_modal2");
@@ -383,7 +409,7 @@ int launch_hex8_modal2(topopt_handle* h, const double* x, double* y, int fin) {
 template <int TYT, int DOT, bool PEER>
 int launch_hex8_ring_t(topopt_handle* h, const double* x, double* y, int fin) {
   constexpr int NST = 4;
-  const Geo& g = h->g;
+  const Geo& g = cur_geo(h);
   constexpr int OWNR = 2 * TYT - 1;
   const int tilesX = (g.NX + 30) / 31, tilesY = (g.NY + OWNR - 1) / OWNR;
   int grid = 148 * (TYT <= 5 ? 2 : 1) * std::max(1, h->kxu_waves);
@@ -399,12 +425,12 @@ int launch_hex8_ring_t(topopt_handle* h, const double* x, double* y, int fin) {
   if (h->modal_cube && h->kxu_cube) {
     static std::atomic<unsigned long long> attr_mask{0};
     TRY(ensure_dyn_smem(h, k_apply_hex8_ring<TYT, NST, DOT, PEER, true>, smem, attr_mask));
-    k_apply_hex8_ring<TYT, NST, DOT, PEER, true><<<grid, 32 * (TYT + 1), smem, h->stream>>>(g, x, y, h->d_E, h->d_fixed, h->fixed_diag, tilesX, tilesY,
+    k_apply_hex8_ring<TYT, NST, DOT, PEER, true><<<grid, 32 * (TYT + 1), smem, h->stream>>>(g, x, y, cur_E(h), cur_fixed(h), h->fixed_diag, tilesX, tilesY,
                                                                                            h->d_partials, h->d_st, fin, xlo, xhi);
   } else {
     static std::atomic<unsigned long long> attr_mask{0};
     TRY(ensure_dyn_smem(h, k_apply_hex8_ring<TYT, NST, DOT, PEER, false>, smem, attr_mask));
-    k_apply_hex8_ring<TYT, NST, DOT, PEER, false><<<grid, 32 * (TYT + 1), smem, h->stream>>>(g, x, y, h->d_E, h->d_fixed, h->fixed_diag, tilesX, tilesY,
+    k_apply_hex8_ring<TYT, NST, DOT, PEER, false><<<grid, 32 * (TYT + 1), smem, h->stream>>>(g, x, y, cur_E(h), cur_fixed(h), h->fixed_diag, tilesX, tilesY,
                                                                                             h->d_partials, h->d_st, fin, xlo, xhi);
   }
   h->stats.kernel_launches += 1;
@@ -420,7 +446,7 @@ inline int ring_rows(const topopt_handle* h) {
   const int cand[3] = {11, 10, 8};
   for (int k = 0; k < 3; ++k) {
     const int own = 2 * cand[k] - 1;
-    const long long rows = (long long)((h->g.NY + own - 1) / own) * 2 * cand[k];
+    const long long rows = (long long)((cur_geo(h).NY + own - 1) / own) * 2 * cand[k];
     if (best < 0 || rows < best) {
       best = rows;
       tyt = cand[k];
@@ -430,7 +456,7 @@ inline int ring_rows(const topopt_handle* h) {
 }
 
 inline bool use_ring(const topopt_handle* h) {
-  return h->kxu_ring != 0 && h->dim == 3 && h->nc == 3 && h->modal_ok && h->g.nown >= h->kxu_ring_min;
+  return h->kxu_ring != 0 && h->dim == 3 && h->nc == 3 && h->modal_ok && cur_geo(h).nown >= h->kxu_ring_min;
 }
 
 template <int DOT, bool PEER>
@@ -447,7 +473,7 @@ template <bool DOT, bool FUSEP, bool PEER = false>
 int launch_hex8(topopt_handle* h, const double* x, double* y, int fin, const double* r, double* pnew) {
   // Two node rows per thread win on thick slabs (single GPU: +6 %); on thin slabs (>= 4 ranks at
   // config 4) the persistent CTAs' segments get short and the one-row kernel measured 8-15 % faster.
-  if (h->kxu_2row && !FUSEP && (h->kxu_2row != 1 || h->g.nown >= 96)) {
+  if (h->kxu_2row && !FUSEP && (h->kxu_2row != 1 || cur_geo(h).nown >= 96)) {
     int tyt = h->kxu_2row;
     if (tyt == 1) {  // auto: thread rows per CTA that waste the fewest node rows for this grid
       double best = -1.0;
@@ -455,8 +481,8 @@ int launch_hex8(topopt_handle* h, const double* x, double* y, int fin, const dou
       const double speed[3] = {1.0, 0.97, 0.93};  // measured relative efficiency of the variants
       for (int k = 0; k < 3; ++k) {
         const int rows = 2 * cand[k] - 2;
-        const int tiles = (h->g.NY + rows - 1) / rows;
-        const double eff = speed[k] * (double)h->g.NY / ((double)tiles * (rows + 2));
+        const int tiles = (cur_geo(h).NY + rows - 1) / rows;
+        const double eff = speed[k] * (double)cur_geo(h).NY / ((double)tiles * (rows + 2));
         if (eff > best) {
           best = eff;
           tyt = cand[k];
@@ -482,9 +508,9 @@ int launch_hex8(topopt_handle* h, const double* x, double* y, int fin, const dou
 template <bool DOT>
 int launch_apply(topopt_handle* h, const double* x, double* y, int fin) {
   if (h->dim == 3 && h->nc == 3 && h->modal_ok) return launch_hex8<DOT, false>(h, x, y, fin, nullptr, nullptr);
-  const int grid = grid_for((long long)h->g.S * h->g.nown, DOT ? kReduceBlocks : kWideGrid);
+  const int grid = grid_for((long long)cur_geo(h).S * cur_geo(h).nown, DOT ? kReduceBlocks : kWideGrid);
 #define CALL(D, C) \
-  LAUNCH(h, (k_apply<D, C, DOT>), grid, h->g, x, y, h->d_E, h->d_fixed, h->fixed_diag, h->d_partials, h->d_st, fin)
+  LAUNCH(h, (k_apply<D, C, DOT>), grid, cur_geo(h), x, y, cur_E(h), cur_fixed(h), h->fixed_diag, h->d_partials, h->d_st, fin)
   DISPATCH(h, CALL);
 #undef CALL
   return check_launch(h, "k_apply");
