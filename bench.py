@@ -104,13 +104,13 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def ncu_traffic(world):
+def ncu_traffic(world, key="kxu_dram_bytes_per_launch"):
     """dram__bytes_read.sum + dram__bytes_write.sum per K.u launch from the committed ncu capture
     (profiles/ncu_traffic.json); only recorded for the single-GPU configuration-4 kernel."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             d = json.load(f)
-        return d.get(f"n{world}", {}).get("kxu_dram_bytes_per_launch")
+        return d.get(f"n{world}", {}).get(key)
     except Exception:
         return None
 
@@ -339,7 +339,9 @@ def run_native(args, nels):
     ring = nown >= int(os.environ.get("TOPOPT_KXU_RING_MIN", "12")) and os.environ.get("TOPOPT_KXU_RING", "1") != "0"
     kxu_which = 8 if (single and ring) else 0
     kxu_ms = solver.time_kernel(kxu_which, args.kernel_reps)
-    cg_ms = solver.time_kernel(9 if single and ring else 1, args.kernel_reps)
+    cg_ms = solver.time_kernel(9 if single and ring else 1, max(args.kernel_reps, 200))
+    # single GPU + single-pass recurrence: the whole CG iteration is ONE kernel (kxu_hex8_cgfused.cuh); it is the dominant kernel
+    fused = single and ring and world == 1 and os.environ.get("TOPOPT_CG_FUSED", "1") != "0"
     cg_ref_ms = solver.time_kernel(1, args.kernel_reps)
     kxu_prev_ms = solver.time_kernel(7, args.kernel_reps)
     sens_ms = solver.time_kernel(2, 5)
@@ -354,7 +356,23 @@ def run_native(args, nels):
     kxu_bytes_total = 16 * prob.ndof + 8 * prob.nel  # read x, write y, read E_e
     kxu_bytes_launch = kxu_bytes_total / world       # one launch per rank over its slab
     achieved = kxu_bytes_launch / (kxu_ms * 1e-3) / 1e9
-    cg_bytes = (80 * prob.ndof + 8 * prob.nel) / world
+    cg_bytes = ((64 if fused else (72 if single and ring else 88)) * prob.ndof + 8 * prob.nel) / world  # bytes one iteration moves
+    kxu_alone = {"kernel": kxu_name, "algorithmic_bytes_per_launch": kxu_bytes_launch, "ms_per_launch": kxu_ms, "achieved": achieved,
+                 "frac": achieved / peak, "traffic": ncu_traffic(world) if nels == DEFAULT_NELS else None,
+                 "previous_generation_ms": kxu_prev_ms,
+                 "timed_on": "dense direction vector (zero on prescribed dofs), fused dot products; launched once per solve when the iteration is one kernel"}
+    if fused:
+        # read p, r, Ap, x and write p, r, Ap, x (64 B per dof) + E_e (8 B per element): DESIGN.md section 4
+        roof_name = ("k_cg_fused_hex8 (one CG iteration per launch: x += a p, r -= a Ap, p = r + b p applied while the planes are staged, "
+                     "matrix-free hex8 K.p, fused p.Ap / Ap.Ap / r.r and scalar step)")
+        roof_bytes = 64 * prob.ndof + 8 * prob.nel
+        roof_ms = cg_ms
+        roof_traffic = ncu_traffic(world, "cg_fused_dram_bytes_per_launch") if nels == DEFAULT_NELS else None
+        roof_timed = "inside the CG loop on a dense right-hand side (topopt_time_kernel class 9: solve time / iterations, graph-replayed launches)"
+    else:
+        roof_name, roof_bytes, roof_ms, roof_traffic = kxu_name, kxu_bytes_launch, kxu_ms, kxu_alone["traffic"]
+        roof_timed = "dense direction vector (zero on prescribed dofs), fused dot products, the variant the CG loop launches"
+    roof_achieved = roof_bytes / (roof_ms * 1e-3) / 1e9
 
     # ---- BASELINE config 3 (60x20x20) in full, the un-extrapolated twin of the reference arm's figure ----------
     cfg3 = None
@@ -387,9 +405,10 @@ def run_native(args, nels):
                 "cg": {"abstol": 1e-7, "reltol": "sqrt(eps)", "maxiter": args.maxiter, "iters_per_step": iters / args.steps,
                        "converged": bool(res.converged), "residual": res.residual,
                        "recurrence": ("single-pass CG (beta predicted from alpha^2 Ap.Ap - r.r; x, r, p updated in one pass; iterates agree with "
-                                      "IterativeSolvers' cg! to rounding, see reference_recurrence)" if single and ring else "IterativeSolvers cg! recurrence")},
+                                      "IterativeSolvers' cg! to rounding, see reference_recurrence)" if single and ring else "IterativeSolvers cg! recurrence"),
+                       "kernels_per_iteration": 1 if fused else (2 if single and ring else 3)},
                 "parallelism": f"z-slab x{world}" if world > 1 else "single GPU",
-                "l2": "inputs larger than L2 (K.u touches 239 MB, one CG iteration 0.96-1.06 GB per pass)",
+                "l2": "inputs larger than L2 (K.u touches 239 MB, one CG iteration 0.86-1.06 GB)",
                 "objective": obj,
             },
             "clocks": clk.summary(),
@@ -397,17 +416,17 @@ def run_native(args, nels):
                     "d2h_bytes_per_step": int(st2.d2h_bytes // args.steps) + 8, "objective": obj_e2e},
             "gpu_launches": launches,
             "parity_check": parity,
-            "roofline": {"kernel": kxu_name, "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(world) if nels == DEFAULT_NELS else None,
+            "roofline": {"kernel": roof_name, "bound": "hbm", "achieved": roof_achieved, "peak": peak,
+                         "unit": "GB/s", "frac": roof_achieved / peak, "traffic": roof_traffic,
                          "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": kxu_bytes_launch, "ms_per_launch": kxu_ms,
-                         "timed_on": "dense direction vector (zero on prescribed dofs), fused dot products, the variant the CG loop launches",
-                         "previous_generation_ms": kxu_prev_ms},
+                         "algorithmic_bytes_per_launch": roof_bytes, "ms_per_launch": roof_ms,
+                         "timed_on": roof_timed},
+            "kxu_alone": kxu_alone,
             "kxu_gdofs": prob.ndof / (kxu_ms * 1e-3) / 1e9,
             "cg_iteration": {"ms": cg_ms, "it_per_s": 1e3 / cg_ms, "achieved_gbs": cg_bytes / (cg_ms * 1e-3) / 1e9,
                              "frac_of_hbm": cg_bytes / (cg_ms * 1e-3) / 1e9 / peak,
                              "reference_recurrence_ms": cg_ref_ms,
-                             "bytes_moved_per_iteration": ((72 if single and ring else 88) * prob.ndof + 8 * prob.nel) / world},
+                             "bytes_moved_per_iteration": cg_bytes},
             "kernels_ms": {"kxu": kxu_ms, "cg_iteration": cg_ms, "sensitivity": sens_ms, "filter_forward": filt_ms},
             "solve_ms_per_step": dev_ms / args.steps,
             "reference_recurrence": ref_rec,

@@ -47,7 +47,7 @@ enum { TOPOPT_PENALTY_POWER = 0, TOPOPT_PENALTY_RATIONAL = 1, TOPOPT_PENALTY_SIN
 /* operator used by topopt_solve: CGMatrixFreeSolver / CGAssemblySolver (solvers_api.jl:58,66) */
 enum { TOPOPT_OP_MATRIX_FREE = 0, TOPOPT_OP_ASSEMBLED = 1 };
 /* preconditioner: identity or DiagonalPreconditioner (Preconditioners.jl, solvers_api.jl:187-192) */
-enum { TOPOPT_PRECOND_NONE = 0, TOPOPT_PRECOND_JACOBI = 1 };
+enum { TOPOPT_PRECOND_NONE = 0, TOPOPT_PRECOND_JACOBI = 1, TOPOPT_PRECOND_MULTIGRID = 2 };
 /* CG scalar recurrence.  REFERENCE reproduces IterativeSolvers 0.9 cg! iterate by iterate
  * (three vector passes per iteration).  SINGLE_PASS is the same Krylov method with beta predicted
  * from |r - alpha Ap|^2 = alpha^2 Ap.Ap - r.r, which lets x, r and p be updated in one pass; its
@@ -100,6 +100,9 @@ typedef struct {
                              1 = start from the device-resident solution of the previous solve   */
   int32_t refresh_precond;/* 0 = preconditioner built once per solver like the reference
                              (solvers_api.jl:187-192); 1 = rebuild it from the current stiffness */
+  int32_t mg_degree;      /* TOPOPT_PRECOND_MULTIGRID: Chebyshev smoother degree (0 = default 2)  */
+  int32_t reserved0;
+  double mg_ratio;        /* ... smoothed spectrum [lambda_max/ratio, lambda_max] (0 = default 6) */
 } topopt_cg_opts;
 
 typedef struct {

@@ -53,6 +53,9 @@ struct CGOpts                      # topopt_cg_opts
     variant::Int32                 # 0 = IterativeSolvers' recurrence (default), 1 = single-pass recurrence
     warm_start::Int32              # 0 = zero initial guess like the reference
     refresh_precond::Int32         # 0 = preconditioner built once like the reference
+    mg_degree::Int32               # multigrid preconditioner (precond = 2): Chebyshev degree, 0 = default
+    reserved0::Int32
+    mg_ratio::Float64              # ... smoothed part of the spectrum, 0 = default
 end
 mutable struct CGResult
     iters::Int32; converged::Int32; residual::Float64; tol::Float64; solve_ms::Float64
@@ -60,7 +63,7 @@ mutable struct CGResult
 end
 
 # Opt-in extensions over the reference, process-wide (all off by default so that parity holds)
-const OPTIONS = Dict{Symbol,Int32}(:variant => 0, :warm_start => 0, :refresh_precond => 0)
+const OPTIONS = Dict{Symbol,Int32}(:variant => 0, :warm_start => 0, :refresh_precond => 0, :multigrid => 0)
 
 "Device handle of one solver; destroyed by the GC finalizer."
 mutable struct Handle
@@ -138,8 +141,8 @@ end
 criteria_code(::FEA.DefaultCriteria) = Cint(0)
 criteria_code(::FEA.EnergyCriteria) = Cint(1)
 cgopts(s::GenericFEASolver{T,P,S}; warm=false) where {T,P,S} = CGOpts(s.abstol, sqrt(eps(T)), s.cg_max_iter, opcode(S),
-    s.preconditioner === identity ? 0 : 1, criteria_code(s.conv), 0,
-    OPTIONS[:variant], (warm && OPTIONS[:warm_start] != 0) ? 1 : 0, OPTIONS[:refresh_precond])
+    OPTIONS[:multigrid] != 0 ? 2 : (s.preconditioner === identity ? 0 : 1), criteria_code(s.conv), 0,
+    OPTIONS[:variant], (warm && OPTIONS[:warm_start] != 0) ? 1 : 0, OPTIONS[:refresh_precond], 0, 0, 0.0)
 
 projection(p) = (Cint(0), 0.0)
 projection(p::ProjectedPenaltyFun{<:Any,<:Any,<:HeavisideProjectionFun}) = (Cint(1), Float64(p.proj.β))

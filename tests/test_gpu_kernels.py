@@ -154,6 +154,114 @@ def test_single_pass_cg_matches_reference_recurrence(lib, nels):
     b.close()
 
 
+@pytest.mark.parametrize("nels", [(12, 8, 30), (40, 26, 50), (70, 44, 24)])
+def test_one_kernel_cg_iteration_matches_two_kernel_single_pass(lib, nels, monkeypatch):
+    """kxu_hex8_cgfused.cuh: x, r, p of iteration k-1 are formed while the planes of K.p_k are staged (one launch
+    per iteration, ping-pong p / r / Ap).  Same recurrence as k_apply_hex8_ring + k_update_xrp: iterates agree to
+    rounding (only the summation order of the dot products differs), iteration counts and residuals match, the
+    converged solution meets the oracle, and a second solve on the same handle (graph replay, parity restart) agrees."""
+    t = lib
+    prob, oprob, s0 = make(t, nels)
+    s0.close()
+    rho = rand_rho(prob.nel, 33)
+
+    def mk(fused, **kw):
+        monkeypatch.setenv("TOPOPT_CG_FUSED", "1" if fused else "0")
+        return t.FEASolver(t.CUDAMatrixFreeSolver, prob, penalty=t.PowerPenaltyFun(3.0), cg_variant=1, **kw)
+
+    for maxiter in (1, 2, 5, 20, 61):
+        a, b = mk(False, cg_max_iter=maxiter, abstol=0.0, reltol=0.0), mk(True, cg_max_iter=maxiter, abstol=0.0, reltol=0.0)
+        a.vars = rho
+        b.vars = rho
+        ua, ub = a().copy(), b().copy()
+        la, lb = a.stats().kernel_launches, b.stats().kernel_launches
+        assert a.last_result.iters == b.last_result.iters == maxiter
+        assert rel(ub, ua) < (1e-12 if maxiter <= 5 else 1e-8), maxiter
+        assert abs(a.last_result.residual - b.last_result.residual) <= 1e-8 * a.last_result.residual
+        assert lb < la or maxiter == 1  # one launch per iteration instead of two
+        ub2 = b().copy()  # same handle again: the iteration parity restarts from the first buffer set
+        assert np.array_equal(ub2, ub)
+        a.close()
+        b.close()
+    a, b = mk(False, abstol=1e-10, reltol=0.0, cg_max_iter=20000), mk(True, abstol=1e-10, reltol=0.0, cg_max_iter=20000)
+    ca, cb = t.ComplianceFun(a), t.ComplianceFun(b)
+    va, ga = ca.value_and_grad(rho)
+    vb, gb = cb.value_and_grad(rho)
+    assert a.last_result.converged == 1 and b.last_result.converged == 1
+    assert abs(a.last_result.iters - b.last_result.iters) <= max(3, a.last_result.iters // 20)
+    assert abs(va - vb) / va < 1e-8 and rel(gb, ga) < 1e-8 and rel(b.u, a.u) < 1e-7
+    if oprob.nel < 3000:
+        uref = o.solve_direct(oprob, o.get_rho(rho, 3.0, 1e-3))
+        obj, _, g = o.compliance(oprob, uref, rho, 3.0, 1e-3)
+        assert abs(vb - obj) / obj < 1e-8 and rel(gb, g) < 1e-8
+    a.close()
+    b.close()
+
+
+@pytest.mark.parametrize("nels,grid", [((70, 44, 24), "0"), ((70, 44, 24), "7"), ((70, 44, 24), "37"), ((40, 26, 50), "29"),
+                                       ((70, 44, 24), "3"), ((70, 44, 24), "11"), ((40, 26, 50), "5"), ((256, 128, 128), "0")])
+def test_one_kernel_cg_iteration_dense_rhs(lib, nels, grid, monkeypatch):
+    """A DENSE right-hand side makes every owned dof, every tile halo and every segment boundary of the one-kernel
+    iteration live from the first iteration on (a point load only reaches them after many iterations).  Odd CTA counts
+    (TOPOPT_CG_FUSED_GRID) put segment boundaries inside tile columns and across them.  Against the two-kernel path:
+    iterates <= 1e-12, residual norms <= 1e-11; the 3-iterate also against the oracle / the C port."""
+    t = lib
+    if nels[0] == 256 and os.environ.get("TOPOPT_SKIP_FULL_SIZE") == "1":
+        pytest.skip("full-size config 4 disabled")
+    prob = t.PointLoadCantilever(nels)
+    rho = rand_rho(prob.nel, 44)
+    b = np.random.default_rng(45).standard_normal(prob.ndof)
+    b[prob.prescribed_dofs - 1] = 0.0
+
+    def mk(fused, maxiter):
+        monkeypatch.setenv("TOPOPT_CG_FUSED", "1" if fused else "0")
+        if grid != "0":
+            monkeypatch.setenv("TOPOPT_CG_FUSED_GRID", grid)
+        return t.FEASolver(t.CUDAMatrixFreeSolver, prob, penalty=t.PowerPenaltyFun(3.0), cg_variant=1, cg_max_iter=maxiter, abstol=0.0, reltol=0.0)
+
+    for maxiter in (1, 3, 12, 40):
+        a, f = mk(False, maxiter), mk(True, maxiter)
+        a.set_density(rho)
+        f.set_density(rho)
+        ua, uf = a(rhs=b).copy(), f(rhs=b).copy()
+        assert a.last_result.iters == f.last_result.iters == maxiter
+        assert rel(uf, ua) < 1e-12, (maxiter, rel(uf, ua))
+        assert abs(a.last_result.residual - f.last_result.residual) <= 1e-11 * a.last_result.residual, maxiter
+        if maxiter == 3 and prob.nel < 100000:
+            oprob = o.PointLoadCantilever(nels)
+            uref, it, res = o.solve_matfree(oprob, o.get_rho(rho, 3.0, 1e-3), abstol=0.0, reltol=0.0, maxiter=3, rhs=b)
+            assert rel(uf, uref) < 1e-12 and abs(f.last_result.residual - res) <= 1e-11 * res
+        a.close()
+        f.close()
+
+
+@pytest.mark.parametrize("nels", [(32, 16, 16), (48, 16, 32)])
+def test_multigrid_preconditioned_cg(lib, nels):
+    """Opt-in geometric-multigrid V-cycle preconditioner (the reference only has the stale Jacobi of
+    solvers_api.jl:187-203): same solution as plain CG to the solve tolerance, in far fewer iterations, for a
+    high-contrast SIMP field; the hierarchy follows a change of the densities."""
+    t = lib
+    prob = t.PointLoadCantilever(nels)
+    rho = rand_rho(prob.nel, 5) ** 2  # down to ~0.04 -> E contrast ~1e4 with p = 3
+    mk = lambda pre: t.FEASolver(t.CUDAMatrixFreeSolver, prob, penalty=t.PowerPenaltyFun(3.0), xmin=1e-6, abstol=1e-9, reltol=0.0,
+                                 cg_max_iter=50000, preconditioner=pre)
+    a, b = mk(None), mk("multigrid")
+    a.vars = rho
+    b.vars = rho
+    ua, ub = a().copy(), b().copy()
+    assert a.last_result.converged == 1 and b.last_result.converged == 1
+    assert b.last_result.residual <= 1e-9
+    assert rel(ub, ua) < 1e-6
+    assert b.last_result.iters * 8 < a.last_result.iters, (a.last_result.iters, b.last_result.iters)
+    ca, cb = t.ComplianceFun(a), t.ComplianceFun(b)
+    rho2 = np.clip(rho + 0.2, 0.0, 1.0)
+    va, ga = ca.value_and_grad(rho2)
+    vb, gb = cb.value_and_grad(rho2)  # stiffness changed: coarse operators, diagonals and bounds are rebuilt
+    assert b.last_result.converged == 1 and abs(va - vb) / va < 1e-7 and rel(gb, ga) < 1e-6
+    a.close()
+    b.close()
+
+
 def test_warm_start_and_refreshed_jacobi(lib):
     """Opt-in extensions over the reference (solvers_api.jl:187-203): warm start from the resident solution
     and a Jacobi preconditioner rebuilt from the current stiffness reach the same solution in fewer

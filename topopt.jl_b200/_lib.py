@@ -17,7 +17,7 @@ OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NCCL, ERR_NONFINITE, ERR_NO_DEVICE, ERR_MISMATCH = -1, -2, -3, -4, -5, -6
 PENALTY_POWER, PENALTY_RATIONAL, PENALTY_SINH = 0, 1, 2
 OP_MATRIX_FREE, OP_ASSEMBLED = 0, 1
-PRECOND_NONE, PRECOND_JACOBI = 0, 1
+PRECOND_NONE, PRECOND_JACOBI, PRECOND_MULTIGRID = 0, 1, 2
 CRITERIA_DEFAULT, CRITERIA_ENERGY = 0, 1
 CG_REFERENCE, CG_SINGLE_PASS = 0, 1
 PHYSICS_ELASTICITY, PHYSICS_HEAT = 0, 1
@@ -59,6 +59,9 @@ class CGOpts(C.Structure):
         ("variant", C.c_int32),
         ("warm_start", C.c_int32),
         ("refresh_precond", C.c_int32),
+        ("mg_degree", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("mg_ratio", C.c_double),
     ]
 
 

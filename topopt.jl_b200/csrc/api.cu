@@ -20,6 +20,7 @@
 #include "kxu_hex8.cuh"
 #include "kxu_hex8_2row.cuh"
 #include "kxu_hex8_ring.cuh"
+#include "kxu_hex8_cgfused.cuh"
 #include "multigrid.cuh"
 
 using namespace topopt;
@@ -79,6 +80,7 @@ struct MGHierarchy {
   int* d_loc = nullptr;      // dense dof -> local vector index on the coarsest level
   int ncoarse = 0;
   int degree = 2;            // Chebyshev smoother degree
+  double ratio = 6.0;        // smoothed part of the spectrum: [lambda_max / ratio, lambda_max]
   long long cycles = 0;
 };
 
@@ -104,6 +106,9 @@ struct topopt_handle {
   int kxu_ring = 1;       // ring-staged kernel for premasked inputs (CG directions): 0 = off, 1 = auto, else thread rows
   int kxu_cube = 1;       // ring kernel: use the cubic-cell specialisation of the modal matrix when it applies
   int kxu_ring_min = 12;  // fewest owned node planes per rank for which the ring kernel is selected
+  int kxu_grid = 0;       // ring kernel: explicit CTA count (0 = 148 x waves)
+  int cg_fused_grid = 0;  // one-kernel iteration: explicit CTA count (0 = aligned_grid())
+  int cg_fused = 1;       // single GPU, single-pass recurrence: one kernel per CG iteration (kxu_hex8_cgfused.cuh); 0 = off, else thread rows
   int cg_variant_env = -1;  // TOPOPT_CG_VARIANT overrides topopt_cg_opts.variant (diagnostics)
   double fixed_diag = 0.0, cellvol = 1.0;
   double sizes[3] = {1, 1, 1};
@@ -111,6 +116,7 @@ struct topopt_handle {
   int* d_block = nullptr;
   unsigned char* d_fixed = nullptr;
   double *d_b = nullptr, *d_fload = nullptr, *d_u = nullptr, *d_r = nullptr, *d_p = nullptr, *d_p2 = nullptr, *d_Ap = nullptr;
+  double *d_r2 = nullptr, *d_Ap2 = nullptr;  // ping-pong partners of d_r / d_Ap (fused CG iteration kernel)
   // peer-memory communication (cudaIpc): in-kernel allreduce + direct halo reads
   PeerBlock* d_peerblock = nullptr;  // this rank's block (IPC-exported)
   PeerComm* d_peercomm = nullptr;    // device copy of the mapping table
@@ -413,6 +419,7 @@ int launch_hex8_ring_t(topopt_handle* h, const double* x, double* y, int fin) {
   constexpr int OWNR = 2 * TYT - 1;
   const int tilesX = (g.NX + 30) / 31, tilesY = (g.NY + OWNR - 1) / OWNR;
   int grid = 148 * (TYT <= 5 ? 2 : 1) * std::max(1, h->kxu_waves);
+  if (h->kxu_grid > 0) grid = h->kxu_grid;
   const long long units = (long long)tilesX * tilesY * g.nown;
   if (grid > units) grid = (int)units;
   const size_t smem = hex8_ring_smem(TYT, NST);  // per-warp rings + y exchange
@@ -466,6 +473,84 @@ int launch_hex8_ring(topopt_handle* h, const double* x, double* y, int fin) {
     case 8: return launch_hex8_ring_t<8, DOT, PEER>(h, x, y, fin);
     case 11: return launch_hex8_ring_t<11, DOT, PEER>(h, x, y, fin);
     default: return launch_hex8_ring_t<10, DOT, PEER>(h, x, y, fin);
+  }
+}
+
+// ---- one CG iteration per launch (kxu_hex8_cgfused.cuh) ----
+// CTAs for a z-marching kernel whose units (tile column x plane) are split evenly over the grid: k segments per tile
+// column, so that no CTA straddles two columns (a new column costs two halo planes and a pipeline refill), with
+// tiles * k close below a multiple of the SM count (full waves; the block scheduler evens out slow SMs, which a single
+// static wave cannot).  Measured at config 4 (63 columns x 129 planes): 148 CTAs 246 us, 444 CTAs 214 us, 441 = 63 x 7 207 us.
+inline int aligned_grid(int tiles, int planes) {
+  double best = -1.0;
+  int grid = tiles;
+  for (int k = 1; k <= 16 && (k == 1 || 4 * k <= planes); ++k) {
+    const long long ctas = (long long)tiles * k;
+    const double fill = (double)ctas / (double)(((ctas + 147) / 148) * 148);
+    const double seg = (double)planes / k;
+    const double eff = fill * seg / (seg + 4.0) * (ctas >= 2 * 148 ? 1.0 : 0.93);  // one or two waves: no dynamic balancing
+    if (eff > best) {
+      best = eff;
+      grid = (int)ctas;
+    }
+  }
+  return grid;
+}
+
+// thread rows per CTA: the variant that wastes the fewest node rows among those whose shared memory fits
+inline int fused_rows(const topopt_handle* h) {
+  if (h->cg_fused > 1) return h->cg_fused;
+  long long best = -1;
+  int tyt = 10;
+  const int cand[2] = {10, 8};
+  for (int k = 0; k < 2; ++k) {
+    const int own = 2 * cand[k] - 1;
+    const long long rows = (long long)((h->g.NY + own - 1) / own) * 2 * cand[k];
+    if (best < 0 || rows < best) {
+      best = rows;
+      tyt = cand[k];
+    }
+  }
+  return tyt;
+}
+
+template <int TYT>
+int launch_cg_fused_t(topopt_handle* h, int fin) {
+  constexpr int NST = 4;
+  const Geo& g = h->g;
+  constexpr int OWNR = 2 * TYT - 1;
+  const int tilesX = (g.NX + 30) / 31, tilesY = (g.NY + OWNR - 1) / OWNR;
+  const long long units = (long long)tilesX * tilesY * g.nown;
+  int grid = h->cg_fused_grid > 0 ? h->cg_fused_grid : aligned_grid(tilesX * tilesY, g.nown);
+  if (units < grid) grid = (int)units;
+  const size_t smem = hex8_fused_smem(TYT, NST);
+  CGFusedVecs v;
+  v.p[0] = h->d_p;
+  v.p[1] = h->d_p2;
+  v.r[0] = h->d_r;
+  v.r[1] = h->d_r2;
+  v.ap[0] = h->d_Ap;
+  v.ap[1] = h->d_Ap2;
+  v.x = h->d_u;
+  if (h->modal_cube && h->kxu_cube) {
+    static std::atomic<unsigned long long> attr_mask{0};
+    TRY(ensure_dyn_smem(h, k_cg_fused_hex8<TYT, NST, true>, smem, attr_mask));
+    k_cg_fused_hex8<TYT, NST, true><<<grid, 32 * (TYT + 1), smem, h->stream>>>(g, v, h->d_E, h->d_fixed, h->fixed_diag, tilesX, tilesY,
+                                                                             h->d_partials, h->d_st, fin);
+  } else {
+    static std::atomic<unsigned long long> attr_mask{0};
+    TRY(ensure_dyn_smem(h, k_cg_fused_hex8<TYT, NST, false>, smem, attr_mask));
+    k_cg_fused_hex8<TYT, NST, false><<<grid, 32 * (TYT + 1), smem, h->stream>>>(g, v, h->d_E, h->d_fixed, h->fixed_diag, tilesX, tilesY,
+                                                                              h->d_partials, h->d_st, fin);
+  }
+  h->stats.kernel_launches += 1;
+  return check_launch(h, "k_cg_fused_hex8");
+}
+
+int launch_cg_fused(topopt_handle* h, int fin) {
+  switch (fused_rows(h)) {
+    case 8: return launch_cg_fused_t<8>(h, fin);
+    default: return launch_cg_fused_t<10>(h, fin);
   }
 }
 
@@ -549,10 +634,13 @@ int launch_cg_apply(topopt_handle* h, bool peer_halo, int fin) {
   return launch_apply<true>(h, h->d_p, h->d_Ap, fin);
 }
 
+#include "mg_solve.inl"
+
 // IterativeSolvers cg!: see cg_finalize() for the scalar recurrences.
 // b (local layout) must already be zero on prescribed dofs.
 int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_cg_result* res, bool ignore_convergence = false,
              int fixed_iters = 0) {
+  if (o->precond == TOPOPT_PRECOND_MULTIGRID) return mg_pcg_solve(h, b, o, res);
   const bool assembled = o->op == TOPOPT_OP_ASSEMBLED;
   if (assembled) {
     if (h->world > 1) return fail(h, TOPOPT_ERR_INVALID, "the assembled operator is single-GPU only");
@@ -574,6 +662,8 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
   // single-pass recurrence: identity preconditioner, default criteria, ring-staged K.u, device-side scalars
   int want_variant = h->cg_variant_env >= 0 ? h->cg_variant_env : o->variant;
   const bool single = want_variant == TOPOPT_CG_SINGLE_PASS && !pre && !energy && hex8 && use_ring(h) && (h->world == 1 || peer);
+  // ... and on one GPU the whole iteration is one kernel (vector updates applied while the planes are staged)
+  const bool fused = single && h->world == 1 && h->cg_fused != 0;
   CGState& s = *h->h_st;
   std::memset(&s, 0, sizeof(CGState));
   s.abstol = ignore_convergence ? -1.0 : o->abstol;
@@ -609,6 +699,7 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
     k_finalize<<<1, 1, 0, h->stream>>>(h->d_st, FIN_INIT);
     h->stats.kernel_launches += 1;
   }
+  if (fused) TRY(launch_cg_apply<2>(h, false, FIN_PAP2));  // Ap_0 = K p_0, alpha_0, beta_0: every later iteration is one launch
   int batch = o->check_every > 0 ? o->check_every : (h->ndof > 2000000 ? 25 : 50);
   int issued = 0;
   const int maxiter = s.maxiter;
@@ -632,6 +723,11 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
     auto one_iteration = [&]() -> int {
       launches_per_iter = 0;
       mark();
+      if (fused) {  // r, p, x of the previous step while staging ; K.u ; p.Ap, Ap.Ap, r.r -> alpha, beta, convergence
+        TRY(launch_cg_fused(h, FIN_FUSED));
+        launches_per_iter = 1;
+        return TOPOPT_OK;
+      }
       if (single) {  // K.u (+ p.Ap, Ap.Ap -> alpha, beta) ; x, r, p in one pass (+ r.r)
         TRY(launch_cg_apply<2>(h, peer_halo, FIN_PAP2));
         mark();
@@ -692,11 +788,11 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
       unsigned long long key = 1469598103934665603ULL;
       auto mix = [&](unsigned long long v) { key = (key ^ v) * 1099511628211ULL; };
       for (const void* q : {(const void*)b, (const void*)D, (const void*)h->d_p, (const void*)h->d_u, (const void*)h->d_r,
-                            (const void*)h->d_Ap, (const void*)h->d_E, (const void*)h->d_st})
+                            (const void*)h->d_Ap, (const void*)h->d_E, (const void*)h->d_st, (const void*)h->d_p2})
         mix((unsigned long long)(uintptr_t)q);
       mix((unsigned long long)n);
       mix((unsigned long long)(energy ? 1 : 0) | (assembled ? 2 : 0) | (peer_halo ? 4 : 0) | (peer ? 8 : 0) | (single ? 16 : 0) |
-          (use_ring(h) ? 32 : 0) | ((unsigned long long)ring_rows(h) << 8));
+          (use_ring(h) ? 32 : 0) | (fused ? 64 : 0) | ((unsigned long long)ring_rows(h) << 8) | ((unsigned long long)(fused ? fused_rows(h) : 0) << 16));
       if (h->cg_graph == nullptr || h->cg_graph_key != key) {
         if (h->cg_graph) {
           cudaGraphExecDestroy(h->cg_graph);
@@ -809,6 +905,7 @@ int penalize(topopt_handle* h, int kind, double p, double xmin, int pen_first) {
   LAUNCH(h, k_penalize, grid_for(h->nloc_el, kWideGrid), (long long)h->nloc_el, h->d_rho, h->d_E, h->d_dE, kind, p, xmin,
          pen_first, h->proj_kind, h->proj_beta);
   h->stiffness_dirty = true;
+  h->mg_dirty = true;
   return check_launch(h, "k_penalize");
 }
 
@@ -1088,6 +1185,9 @@ int topopt_create(const topopt_desc* d, topopt_handle** out) {
     if (const char* e = getenv("TOPOPT_KXU_RING")) h->kxu_ring = atoi(e);
     if (const char* e = getenv("TOPOPT_KXU_RING_MIN")) h->kxu_ring_min = atoi(e);
     if (const char* e = getenv("TOPOPT_KXU_CUBE")) h->kxu_cube = atoi(e);
+    if (const char* e = getenv("TOPOPT_CG_FUSED")) h->cg_fused = atoi(e);
+    if (const char* e = getenv("TOPOPT_CG_FUSED_GRID")) h->cg_fused_grid = std::max(1, atoi(e));
+    if (const char* e = getenv("TOPOPT_KXU_GRID")) h->kxu_grid = std::max(1, atoi(e));
   }
   if (const char* e = getenv("TOPOPT_CG_VARIANT")) h->cg_variant_env = atoi(e);
 
@@ -1175,7 +1275,7 @@ int topopt_create(const topopt_desc* d, topopt_handle** out) {
   CTRY(dev_alloc(h, &h->d_partials, (size_t)std::max(kWideGrid * 4, kMaxPartialBlocks)));
   CTRY(dev_alloc(h, &h->d_block, h->nloc_nodes));
   CTRY(dev_alloc(h, &h->d_fixed, h->nloc_nodes));
-  for (double** v : {&h->d_b, &h->d_fload, &h->d_u, &h->d_r, &h->d_p, &h->d_p2, &h->d_Ap, &h->d_D, &h->d_rhs, &h->d_lam, &h->d_tmp})
+  for (double** v : {&h->d_b, &h->d_fload, &h->d_u, &h->d_r, &h->d_p, &h->d_p2, &h->d_Ap, &h->d_r2, &h->d_Ap2, &h->d_D, &h->d_rhs, &h->d_lam, &h->d_tmp})
     CTRY(dev_alloc(h, v, h->nloc_dofs));
   for (double** v : {&h->d_E, &h->d_dE, &h->d_rho, &h->d_cell, &h->d_grad}) CTRY(dev_alloc(h, v, h->nloc_el));
   CTRY(dev_alloc(h, &h->d_full_dof, h->ndof));
@@ -1241,11 +1341,13 @@ int topopt_destroy(topopt_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->cg_graph) cudaGraphExecDestroy(h->cg_graph);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  mg_free(h->mg);
+  h->mg = nullptr;
   for (void* m : h->peer_mapped)
     if (m) cudaIpcCloseMemHandle(m);
   if (h->d_peerblock) cudaFree(h->d_peerblock);
   if (h->d_peercomm) cudaFree(h->d_peercomm);
-  void* ptrs[] = {h->d_block, h->d_fixed, h->d_b, h->d_fload, h->d_u, h->d_r, h->d_p, h->d_p2, h->d_Ap, h->d_D, h->d_rhs, h->d_lam,
+  void* ptrs[] = {h->d_block, h->d_fixed, h->d_b, h->d_fload, h->d_u, h->d_r, h->d_p, h->d_p2, h->d_Ap, h->d_r2, h->d_Ap2, h->d_D, h->d_rhs, h->d_lam,
                   h->d_tmp, h->d_E, h->d_dE, h->d_rho, h->d_cell, h->d_grad, h->d_full_dof, h->d_full_el, h->d_design,
                   h->d_xf, h->d_gfull, h->d_partials, h->d_st, h->d_nbr_start, h->d_rowptr, h->d_col, h->d_nz, h->d_fasm,
                   h->d_dv, h->d_dc, h->d_xnew};
@@ -1299,6 +1401,7 @@ int topopt_set_stiffness(topopt_handle* h, const double* E, const double* dE) {
   TRY(upload_elems(h, E, h->d_E));
   if (dE) TRY(upload_elems(h, dE, h->d_dE));
   h->stiffness_dirty = true;
+  h->mg_dirty = true;
   return sync(h);
 }
 

@@ -85,7 +85,7 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
   return v;
 }
 
-enum { FIN_NONE = 0, FIN_INIT = 1, FIN_PAP = 2, FIN_RR = 3, FIN_PLAIN = 4, FIN_PAP2 = 5, FIN_RR2 = 6 };
+enum { FIN_NONE = 0, FIN_INIT = 1, FIN_PAP = 2, FIN_RR = 3, FIN_PLAIN = 4, FIN_PAP2 = 5, FIN_RR2 = 6, FIN_FUSED = 7 };
 
 // scalar recurrences of IterativeSolvers.cg! (CGIterable / PCGIterable iterate) and the
 // convergence tests of src/FEA/convergence_criteria.jl:26-45, evaluated on the device so the
@@ -107,6 +107,27 @@ __device__ inline void cg_finalize(CGState* st, int which) {
     const double alpha = rho / s[0];
     double rho_next = fma(alpha * alpha, s[1], -rho);
     if (!(rho_next > 0.0)) rho_next = 0.0;  // cancellation at a (near-)exact solve: restart with steepest descent
+    st->alpha = alpha;
+    st->beta = rho_next / rho;
+    return;
+  }
+  if (which == FIN_FUSED) {
+    // One-kernel iteration (kxu_hex8_cgfused.cuh): s = {p.Ap, Ap.Ap, r.r} of the residual, direction and product the
+    // kernel has just formed.  First the end of the iteration that produced r (FIN_RR2), then, unless it converged,
+    // the scalars of the next one (FIN_PAP2).
+    st->prev_res = st->res;
+    st->res = sqrt(s[2]);
+    st->iters += 1;
+    st->rho = s[2];
+    const bool conv = st->res <= st->tol;
+    if (isnan(st->res)) st->nonfinite = 1;
+    st->converged = conv ? 1 : 0;
+    st->done = (conv || st->iters >= st->maxiter || st->nonfinite) ? 1 : 0;
+    st->pAp = s[0];
+    const double rho = s[2];
+    const double alpha = rho / s[0];
+    double rho_next = fma(alpha * alpha, s[1], -rho);
+    if (!(rho_next > 0.0)) rho_next = 0.0;
     st->alpha = alpha;
     st->beta = rho_next / rho;
     return;

@@ -98,32 +98,60 @@ __global__ void k_mg_prolong_add(Geo gf, Geo gc, const double* __restrict__ xc, 
   }
 }
 
-// Chebyshev smoother pieces on owned dofs [off, off + n):
-//   first:  d = (r / D) / theta                       (r = b when the initial guess is zero)
-//   step :  x += d ; r -= Kd ; d = c1 d + c2 (r / D)
-//   last :  x += d
-__global__ void __launch_bounds__(kBlock) k_cheb_first(long long off, long long n, const double* __restrict__ r,
+// Chebyshev smoother pieces on owned dofs [off, off + n)  (Saad, Iterative Methods, Alg. 12.1 with D^-1 K):
+//   first:  [r = b - Kx ;]  d = (r / D) / theta
+//   step :  x (+)= d ; r = rin - Kd ; d = c1 d + c2 (r / D)          (rin may alias r; rin = b on the first step)
+//   last :  x (+)= d ; [r = rin - Kd]
+template <bool RESID>
+__global__ void __launch_bounds__(kBlock) k_cheb_first(long long off, long long n, const double* b, const double* Kx, double* r,
                                                        const double* __restrict__ D, double inv_theta, double* __restrict__ d) {
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
-    d[off + t] = inv_theta * (r[off + t] / D[off + t]);
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const long long k = off + t;
+    double rk = b[k];
+    if (RESID) {
+      rk -= Kx[k];
+      r[k] = rk;
+    }
+    d[k] = inv_theta * (rk / D[k]);
+  }
 }
 template <bool ZERO_X>
-__global__ void __launch_bounds__(kBlock) k_cheb_step(long long off, long long n, double* __restrict__ x, double* __restrict__ r,
+__global__ void __launch_bounds__(kBlock) k_cheb_step(long long off, long long n, double* __restrict__ x, const double* rin, double* r,
                                                       double* __restrict__ d, const double* __restrict__ Kd,
                                                       const double* __restrict__ D, double c1, double c2) {
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
     const long long k = off + t;
     const double dk = d[k];
-    const double rk = r[k] - Kd[k];
+    const double rk = rin[k] - Kd[k];
     x[k] = ZERO_X ? dk : x[k] + dk;
     r[k] = rk;
     d[k] = fma(c1, dk, c2 * (rk / D[k]));
   }
 }
-template <bool ZERO_X>
-__global__ void __launch_bounds__(kBlock) k_cheb_last(long long off, long long n, double* __restrict__ x, const double* __restrict__ d) {
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
-    x[off + t] = ZERO_X ? d[off + t] : x[off + t] + d[off + t];
+template <bool ZERO_X, bool RESID>
+__global__ void __launch_bounds__(kBlock) k_cheb_last(long long off, long long n, double* __restrict__ x, const double* __restrict__ d,
+                                                      const double* rin, double* r, const double* __restrict__ Kd) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const long long k = off + t;
+    x[k] = ZERO_X ? d[k] : x[k] + d[k];
+    if (RESID) r[k] = rin[k] - Kd[k];
+  }
+}
+
+// outer PCG: x += alpha p ; r -= alpha Ap ; sum r.r -> st->sums[0]
+__global__ void __launch_bounds__(kBlock) k_mg_update_xr(long long off, long long n, double* __restrict__ x, double* __restrict__ r,
+                                                         const double* __restrict__ p, const double* __restrict__ Ap, double alpha,
+                                                         double* partials, CGState* st) {
+  __shared__ double sm[32];
+  double v[1] = {0.0};
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const long long k = off + t;
+    x[k] = fma(alpha, p[k], x[k]);
+    const double rk = fma(-alpha, Ap[k], r[k]);
+    r[k] = rk;
+    v[0] = fma(rk, rk, v[0]);
+  }
+  block_partials_finish<1>(v, partials, st, FIN_PLAIN, sm);
 }
 
 // coarsest level: x = Ainv b (dense, n <= ~1500), one warp per row

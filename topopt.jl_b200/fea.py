@@ -185,7 +185,14 @@ class GenericFEASolver:
         o.reltol = over.get("reltol", self.reltol)
         o.maxiter = over.get("maxiter", self.cg_max_iter)
         o.op = self.solver_type.op
-        o.precond = _lib.PRECOND_NONE if self.preconditioner in (None, "identity") else _lib.PRECOND_JACOBI
+        if self.preconditioner in (None, "identity"):
+            o.precond = _lib.PRECOND_NONE
+        elif self.preconditioner == "multigrid":  # extension: geometric multigrid V-cycle, rebuilt when the stiffness changes
+            o.precond = _lib.PRECOND_MULTIGRID
+            o.mg_degree = int(over.get("mg_degree", getattr(self, "mg_degree", 0)))
+            o.mg_ratio = float(over.get("mg_ratio", getattr(self, "mg_ratio", 0.0)))
+        else:
+            o.precond = _lib.PRECOND_JACOBI
         o.criteria = self.conv.code
         o.check_every = over.get("check_every", self.check_every)
         o.variant = over.get("variant", self.cg_variant)
@@ -212,7 +219,7 @@ class GenericFEASolver:
         """solver(): upload vars, CG solve, write solver.u (or ``lhs`` for a caller-supplied rhs).
         A 2-D ``rhs`` solves every column with a zero initial guess (solvers_api.jl:294-350)."""
         self.set_density()
-        if not self.preconditioner_initialized and self.preconditioner not in (None, "identity"):
+        if not self.preconditioner_initialized and self.preconditioner not in (None, "identity", "multigrid"):
             # UpdatePreconditioner! runs once per solver lifetime (solvers_api.jl:187-192)
             self._check(self._lib.topopt_set_jacobi(self._handle, None))
             self.preconditioner_initialized = True
