@@ -357,6 +357,43 @@ def test_config4_full_size_against_c_port(lib):
     s.close()
 
 
+@pytest.mark.skipif(os.environ.get("TOPOPT_SKIP_FULL_SIZE") == "1", reason="full-size config 4 disabled")
+def test_config4_converged_solution_verified_by_c_port(lib):
+    """North-star acceptance at full size: the multigrid-preconditioned solve of config 4 (12.8 M dofs) to |r| <= 1e-8 is
+    checked a posteriori with the C port of the reference operator: |f - K_port u| <= 2e-8 (the port's own matrix-free
+    mul!, matrix_free_operator.jl:66-105), compliance u'K_port u = f'u to 1e-9, and the compliance of the plain-CG
+    solve at the same tolerance agrees to 1e-8."""
+    import ref_c
+
+    t = lib
+    nels = (256, 128, 128)
+    prob = t.PointLoadCantilever(nels)
+    R = ref_c.RefProblem(3, 3, nels, prob.Ke, prob.prescribed_dofs, openmp=True, native=True)
+    rho = 0.2 + 0.8 * ((np.arange(prob.nel, dtype=np.int64) * 2654435761 % 1000003) / 1000003.0)
+    R.set_density(rho, 3.0, 1e-6)
+    b = prob.fixedload.copy()
+    b[prob.prescribed_dofs - 1] = 0.0
+    mk = lambda pre, mi: t.FEASolver(t.CUDAMatrixFreeSolver, prob, penalty=t.PowerPenaltyFun(3.0), xmin=1e-6, abstol=1e-8, reltol=0.0,
+                                     cg_max_iter=mi, preconditioner=pre, cg_variant=1)
+    s = mk("multigrid", 500)
+    s.vars = rho
+    u = s().copy()
+    assert s.last_result.converged == 1 and s.last_result.iters < 100
+    r = b - R.mul(u)
+    r[prob.prescribed_dofs - 1] = 0.0
+    assert np.linalg.norm(r) <= 2e-8
+    c_mg = float(b @ u)
+    assert abs(float(u @ R.mul(u)) - c_mg) <= 1e-9 * c_mg
+    s.close()
+    s = mk(None, 30000)
+    s.vars = rho
+    u2 = s().copy()
+    assert s.last_result.converged == 1
+    assert abs(float(b @ u2) - c_mg) <= 1e-8 * c_mg
+    R.close()
+    s.close()
+
+
 def test_plain_c_harness_drives_the_abi(lib, tmp_path):
     """The boundary is a C ABI: a plain C99 program (tests/c/harness.c) creates the handle, sets the density,
     solves, evaluates compliance / sensitivities / u'Ku, filters and runs the fused SIMP evaluation -- on every

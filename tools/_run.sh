@@ -1,10 +1,10 @@
-timeout 1200 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k "dense_rhs or one_kernel" 2>&1 | tail -30 > gpurun_out/r02_fused_t7.log
-cat gpurun_out/r02_fused_t7.log
-timeout 900 python tools/r02_probe_fused.py 256,128,128 TOPOPT_CG_FUSED=1 TOPOPT_CG_FUSED=0 > gpurun_out/r02_fused_p10.log 2>&1
-cat gpurun_out/r02_fused_p10.log
-timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_n1_c.json 2> gpurun_out/r02_bench_n1_c.err
+timeout 1500 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k "multigrid or verified_by_c_port" 2>&1 | tail -30 > gpurun_out/r02_mg_t1.log
+cat gpurun_out/r02_mg_t1.log
+timeout 1500 python tools/r02_probe_mg.py 256,128,128 1e-8 2:6 3:8 3:15 4:20 > gpurun_out/r02_mg_p2.log 2>&1
+grep MG gpurun_out/r02_mg_p2.log
+timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/r02_bench_n1_d.json 2> gpurun_out/r02_bench_n1_d.err
 python -c "
 import json
-d=json.load(open('gpurun_out/r02_bench_n1_c.json'))
-print(d['value'], d['config']['cg'], d['reference_recurrence'], d['converged_run'])
+d=json.load(open('gpurun_out/r02_bench_n1_d.json'))
+print(d['value'], d['e2e'], d['multigrid_run'], d['converged_run'])
 "

@@ -238,7 +238,7 @@ static int mg_refresh(topopt_handle* h) {
 #undef CALL
     double nrm2 = 0.0, lam = 1.0;
     TRY(mg_dot(h, L, L.d, L.d, &nrm2));
-    const int its = 10;
+    const int its = 15;
     for (int k = 0; k < its; ++k) {
       TRY(mg_apply_level(h, l, L.d, L.t));
       LAUNCH(h, k_scale_inv, grid_for(L.nown_dofs), L.off, L.nown_dofs, L.t, L.D, 1.0 / std::sqrt(nrm2), L.d);  // d = D^-1 K v / |v|
@@ -248,7 +248,7 @@ static int mg_refresh(topopt_handle* h) {
       lam = std::sqrt(n2);  // |D^-1 K v| / |v| with |v| = 1 after the scaling
       nrm2 = n2;
     }
-    L.lmax = 1.1 * lam;
+    L.lmax = 1.2 * lam;  // power iteration approaches lambda_max from below
   }
   TRY(mg_coarse_inverse(h));
   h->mg_dirty = false;
@@ -358,19 +358,28 @@ static int mg_pcg_solve(topopt_handle* h, const double* b, const topopt_cg_opts*
   int iters = 0;
   bool conv = resn <= tol, bad = !std::isfinite(resn);
   double rz_old = 1.0;
+  int restarts = 0;
+  bool fresh = true;  // next direction is the preconditioned residual itself
   while (!conv && !bad && iters < o->maxiter) {
     TRY(mg_vcycle(h, 0, h->d_r));
     m->cycles += 1;
     double rz = 0.0;
     TRY(mg_dot(h, L0, h->d_r, L0.x, &rz));
-    const double beta = iters == 0 ? 0.0 : rz / rz_old;
+    const double beta = fresh ? 0.0 : rz / rz_old;
+    fresh = false;
     LAUNCH(h, k_axpby, vgrid, off, n, 1.0, L0.x, beta, h->d_p, h->d_p);  // p = z + beta p
     TRY(launch_cg_apply<1>(h, false, FIN_NONE));                         // Ap = K p, sums[0] = p.Ap
     double pAp = 0.0;
     TRY(mg_host_scalar(h, &pAp));
     if (!(pAp > 0.0) || !(rz > 0.0)) {
       bad = !std::isfinite(pAp) || !std::isfinite(rz);
-      break;  // direction lost (exact solve or breakdown): stop with the current residual
+      if (bad || restarts >= 4) break;
+      // r.M^-1 r <= 0: the cycle was not positive definite, i.e. a smoother bound was too low for this stiffness.
+      // x and r are still consistent: raise the bounds and restart the recurrence from the current iterate.
+      for (MGLevel& L : m->lv) L.lmax *= 1.3;
+      restarts += 1;
+      fresh = true;
+      continue;
     }
     const double alpha = rz / pAp;
     LAUNCH(h, k_mg_update_xr, vgrid, off, n, h->d_u, h->d_r, h->d_p, h->d_Ap, alpha, h->d_partials, h->d_st);
