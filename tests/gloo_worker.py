@@ -32,9 +32,9 @@ def main():
         print(f"rank {rank}: nccl id unavailable here ({type(e).__name__}); skipping id check")
     # the cudaIpc blob exchange (topopt_ipc_export -> all_gather_bytes -> topopt_ipc_import):
     # equal-sized blobs must come back concatenated in rank order on every rank
-    blob = bytes([rank]) * 132
+    blob = bytes([rank]) * 452
     allb = comm.all_gather_bytes(blob)
-    assert len(allb) == 132 * world and all(allb[132 * r:132 * (r + 1)] == bytes([r]) * 132 for r in range(world))
+    assert len(allb) == 452 * world and all(allb[452 * r:452 * (r + 1)] == bytes([r]) * 452 for r in range(world))
     for nels in ((6, 4, 5), (5, 7)):
         prob = o.PointLoadCantilever(nels) if len(nels) == 3 and nels[2] % 2 == 0 else o.HalfMBB(nels)
         g = prob.grid

@@ -80,6 +80,31 @@ def main():
             s.close(); s2.close()
         for k in env:
             os.environ.pop(k, None)
+    # one-kernel CG iteration across ranks (ghost planes of p, r, Ap of both parities read from the neighbours): dense
+    # right-hand side, multi-tile grid, against the two-kernel path and the oracle
+    nels = (40, 26, 30 * comm.world)
+    prob, oprob = t.PointLoadCantilever(nels), o.PointLoadCantilever(nels)
+    prob.Ke = oprob.Ke.copy()
+    rho = np.random.default_rng(9).uniform(0.2, 1.0, prob.nel)
+    b = np.random.default_rng(10).standard_normal(prob.ndof)
+    b[prob.prescribed_dofs - 1] = 0.0
+    for maxiter in (1, 3, 12, 40):
+        sols = []
+        for fused in ("1", "0"):
+            os.environ["TOPOPT_CG_FUSED_MGPU"] = fused
+            s = t.FEASolver(t.CUDAMatrixFreeSolver, prob, penalty=t.PowerPenaltyFun(3.0), abstol=0.0, reltol=0.0, cg_max_iter=maxiter,
+                            device=local, comm=comm, cg_variant=1)
+            s.set_density(rho)
+            sols.append((s(rhs=b).copy(), s.last_result.residual, s.stats().kernel_launches))
+            assert s.last_result.iters == maxiter
+            s.close()
+        os.environ.pop("TOPOPT_CG_FUSED_MGPU", None)
+        (uf, rf, lf), (ua, ra, la) = sols
+        assert rel(uf, ua) < (1e-12 if maxiter <= 12 else 1e-9) and abs(rf - ra) <= 1e-11 * ra, (maxiter, rel(uf, ua), rf, ra)
+        assert lf < la or maxiter == 1, (lf, la)  # the fused path really ran
+        if maxiter == 3:
+            uo3, it, res = o.solve_matfree(oprob, o.get_rho(rho, 3.0, 1e-3), abstol=0.0, reltol=0.0, maxiter=3, rhs=b)
+            assert rel(uf, uo3) < 1e-12 and abs(rf - res) <= 1e-11 * res
     import torch.distributed as dist
 
     dist.barrier()

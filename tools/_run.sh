@@ -1,8 +1,10 @@
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_cg_fused -s 2 -c 1 -f -o gpurun_out/r02_fused_final python tools/profile_ring.py 256,128,128 9 > gpurun_out/ncu_fused_final.log 2>&1
-tail -2 gpurun_out/ncu_fused_final.log
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r02_launches_bench.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-converged-run > gpurun_out/r02_bench_under_ncu.log 2>&1
-wc -l gpurun_out/r02_launches_bench.csv
-TOPOPT_SKIP_FULL_SIZE=1 timeout 1200 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "one_kernel_cg_iteration_matches or multigrid" > gpurun_out/r02_memcheck_fused.log 2>&1
-tail -5 gpurun_out/r02_memcheck_fused.log
-TOPOPT_SKIP_FULL_SIZE=1 timeout 1200 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "dense_rhs and nels1" > gpurun_out/r02_racecheck_fused.log 2>&1
-tail -8 gpurun_out/r02_racecheck_fused.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node=8 --master-addr 127.0.0.1 --master-port 29517 tests/mgpu_worker.py > gpurun_out/r02_mgpu8_fused.log 2>&1
+grep "MGPU_OK\|AssertionError" gpurun_out/r02_mgpu8_fused.log | head -3
+for f in 1 0; do
+TOPOPT_CG_FUSED_MGPU=$f timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node=8 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 8 --steps 3 --warmup 3 --no-converged-run > gpurun_out/r02_bench_n8_fused$f.json 2> gpurun_out/r02_bench_n8_fused$f.err
+python -c "
+import json
+d=json.load(open('gpurun_out/r02_bench_n8_fused$f.json'))
+print('fused=$f', d['value'], d['e2e']['value'], d['cg_iteration']['ms'], d['parity_check']['ok'], d['config']['objective'])
+" || tail -5 gpurun_out/r02_bench_n8_fused$f.err
+done

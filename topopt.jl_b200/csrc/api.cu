@@ -108,6 +108,7 @@ struct topopt_handle {
   int kxu_ring_min = 12;  // fewest owned node planes per rank for which the ring kernel is selected
   int kxu_grid = 0;       // ring kernel: explicit CTA count (0 = 148 x waves)
   int cg_fused_grid = 0;  // one-kernel iteration: explicit CTA count (0 = aligned_grid())
+  bool cg_fused_single_only = false;  // TOPOPT_CG_FUSED_MGPU=0: ranks of a multi-GPU run keep the two-kernel iteration
   int cg_fused = 1;       // single GPU, single-pass recurrence: one kernel per CG iteration (kxu_hex8_cgfused.cuh); 0 = off, else thread rows
   int cg_variant_env = -1;  // TOPOPT_CG_VARIANT overrides topopt_cg_opts.variant (diagnostics)
   double fixed_diag = 0.0, cellvol = 1.0;
@@ -121,6 +122,11 @@ struct topopt_handle {
   PeerBlock* d_peerblock = nullptr;  // this rank's block (IPC-exported)
   PeerComm* d_peercomm = nullptr;    // device copy of the mapping table
   void* peer_mapped[3 * kMaxRanks] = {nullptr};
+  // the neighbours' p, p2, r, r2, Ap, Ap2 (mapped over cudaIpc) for the one-kernel CG iteration; [0] duplicates peer_p_*
+  const double* peer_lo[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const double* peer_hi[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  void* peer_mapped_vec[2][6] = {{nullptr}};
+  bool peer_fused_ready = false;
   const double* peer_p_lo = nullptr;   // lower neighbour's d_p (mapped)
   const double* peer_p_hi = nullptr;   // upper neighbour's d_p (mapped)
   bool peer_ready = false;
@@ -514,7 +520,7 @@ inline int fused_rows(const topopt_handle* h) {
   return tyt;
 }
 
-template <int TYT>
+template <int TYT, bool PEER>
 int launch_cg_fused_t(topopt_handle* h, int fin) {
   constexpr int NST = 4;
   const Geo& g = h->g;
@@ -532,26 +538,32 @@ int launch_cg_fused_t(topopt_handle* h, int fin) {
   v.ap[0] = h->d_Ap;
   v.ap[1] = h->d_Ap2;
   v.x = h->d_u;
+  for (int k = 0; k < 3; ++k)
+    for (int par = 0; par < 2; ++par) {
+      const double* lo = PEER ? h->peer_lo[2 * k + par] : nullptr;
+      const double* hi = PEER ? h->peer_hi[2 * k + par] : nullptr;
+      v.lo[k][par] = lo ? lo + (size_t)h->plane_dofs * h->nown_lower : nullptr;  // the lower neighbour's top owned plane
+      v.hi[k][par] = hi ? hi + (size_t)h->plane_dofs : nullptr;                  // the upper neighbour's first owned plane
+    }
   if (h->modal_cube && h->kxu_cube) {
     static std::atomic<unsigned long long> attr_mask{0};
-    TRY(ensure_dyn_smem(h, k_cg_fused_hex8<TYT, NST, true>, smem, attr_mask));
-    k_cg_fused_hex8<TYT, NST, true><<<grid, 32 * (TYT + 1), smem, h->stream>>>(g, v, h->d_E, h->d_fixed, h->fixed_diag, tilesX, tilesY,
-                                                                             h->d_partials, h->d_st, fin);
+    TRY(ensure_dyn_smem(h, k_cg_fused_hex8<TYT, NST, true, PEER>, smem, attr_mask));
+    k_cg_fused_hex8<TYT, NST, true, PEER><<<grid, 32 * (TYT + 1), smem, h->stream>>>(g, v, h->d_E, h->d_fixed, h->fixed_diag, tilesX,
+                                                                                   tilesY, h->d_partials, h->d_st, fin);
   } else {
     static std::atomic<unsigned long long> attr_mask{0};
-    TRY(ensure_dyn_smem(h, k_cg_fused_hex8<TYT, NST, false>, smem, attr_mask));
-    k_cg_fused_hex8<TYT, NST, false><<<grid, 32 * (TYT + 1), smem, h->stream>>>(g, v, h->d_E, h->d_fixed, h->fixed_diag, tilesX, tilesY,
-                                                                              h->d_partials, h->d_st, fin);
+    TRY(ensure_dyn_smem(h, k_cg_fused_hex8<TYT, NST, false, PEER>, smem, attr_mask));
+    k_cg_fused_hex8<TYT, NST, false, PEER><<<grid, 32 * (TYT + 1), smem, h->stream>>>(g, v, h->d_E, h->d_fixed, h->fixed_diag, tilesX,
+                                                                                    tilesY, h->d_partials, h->d_st, fin);
   }
   h->stats.kernel_launches += 1;
   return check_launch(h, "k_cg_fused_hex8");
 }
 
-int launch_cg_fused(topopt_handle* h, int fin) {
-  switch (fused_rows(h)) {
-    case 8: return launch_cg_fused_t<8>(h, fin);
-    default: return launch_cg_fused_t<10>(h, fin);
-  }
+int launch_cg_fused(topopt_handle* h, bool peer, int fin) {
+  const int rows = fused_rows(h);
+  if (peer) return rows == 8 ? launch_cg_fused_t<8, true>(h, fin) : launch_cg_fused_t<10, true>(h, fin);
+  return rows == 8 ? launch_cg_fused_t<8, false>(h, fin) : launch_cg_fused_t<10, false>(h, fin);
 }
 
 template <bool DOT, bool FUSEP, bool PEER = false>
@@ -663,7 +675,7 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
   int want_variant = h->cg_variant_env >= 0 ? h->cg_variant_env : o->variant;
   const bool single = want_variant == TOPOPT_CG_SINGLE_PASS && !pre && !energy && hex8 && use_ring(h) && (h->world == 1 || peer);
   // ... and on one GPU the whole iteration is one kernel (vector updates applied while the planes are staged)
-  const bool fused = single && h->world == 1 && h->cg_fused != 0;
+  const bool fused = single && h->cg_fused != 0 && (h->world == 1 || (peer_halo && h->peer_fused_ready && !h->cg_fused_single_only));
   CGState& s = *h->h_st;
   std::memset(&s, 0, sizeof(CGState));
   s.abstol = ignore_convergence ? -1.0 : o->abstol;
@@ -699,7 +711,8 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
     k_finalize<<<1, 1, 0, h->stream>>>(h->d_st, FIN_INIT);
     h->stats.kernel_launches += 1;
   }
-  if (fused) TRY(launch_cg_apply<2>(h, false, FIN_PAP2));  // Ap_0 = K p_0, alpha_0, beta_0: every later iteration is one launch
+  // Ap_0 = K p_0, alpha_0, beta_0: every later iteration is one launch (multi-GPU: and tell the neighbours Ap_0 is final)
+  if (fused) TRY(launch_cg_apply<2>(h, peer_halo, FIN_PAP2 | (peer_halo ? 0x100 : 0)));
   int batch = o->check_every > 0 ? o->check_every : (h->ndof > 2000000 ? 25 : 50);
   int issued = 0;
   const int maxiter = s.maxiter;
@@ -724,7 +737,7 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
       launches_per_iter = 0;
       mark();
       if (fused) {  // r, p, x of the previous step while staging ; K.u ; p.Ap, Ap.Ap, r.r -> alpha, beta, convergence
-        TRY(launch_cg_fused(h, FIN_FUSED));
+        TRY(launch_cg_fused(h, peer_halo, FIN_FUSED));
         launches_per_iter = 1;
         return TOPOPT_OK;
       }
@@ -775,7 +788,7 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
     };
     // multi-GPU single-pass recurrence: the last iteration's r.r is posted but not collected yet
     auto flush_batch = [&]() {
-      if (single && peer) {
+      if (single && peer && !fused) {
         k_cg_flush<<<1, 32, 0, h->stream>>>(h->d_st);
         h->stats.kernel_launches += 1;
       }
@@ -998,15 +1011,20 @@ int topopt_ipc_export(topopt_handle* h, void* out, int64_t* nbytes) {
     CUDA_TRY(h, cudaMalloc((void**)&h->d_peerblock, sizeof(PeerBlock)));
     CUDA_TRY(h, cudaMemset(h->d_peerblock, 0, sizeof(PeerBlock)));
   }
-  cudaIpcMemHandle_t hb, hp;
+  // blob: PeerBlock handle, handles of p, p2, r, r2, Ap, Ap2, owned plane count
+  cudaIpcMemHandle_t hb;
   CUDA_TRY(h, cudaIpcGetMemHandle(&hb, h->d_peerblock));
-  CUDA_TRY(h, cudaIpcGetMemHandle(&hp, h->d_p));
   char* o = static_cast<char*>(out);
   std::memcpy(o, &hb, sizeof(hb));
-  std::memcpy(o + sizeof(hb), &hp, sizeof(hp));
+  double* vecs[6] = {h->d_p, h->d_p2, h->d_r, h->d_r2, h->d_Ap, h->d_Ap2};
+  for (int k = 0; k < 6; ++k) {
+    cudaIpcMemHandle_t hv;
+    CUDA_TRY(h, cudaIpcGetMemHandle(&hv, vecs[k]));
+    std::memcpy(o + (1 + k) * sizeof(hb), &hv, sizeof(hv));
+  }
   const int32_t nown = h->g.nown;
-  std::memcpy(o + 2 * sizeof(hb), &nown, sizeof(nown));
-  *nbytes = 2 * sizeof(hb) + sizeof(nown);
+  std::memcpy(o + 7 * sizeof(hb), &nown, sizeof(nown));
+  *nbytes = 7 * sizeof(hb) + sizeof(nown);
   return TOPOPT_OK;
 }
 
@@ -1014,7 +1032,7 @@ int topopt_ipc_export(topopt_handle* h, void* out, int64_t* nbytes) {
 int topopt_ipc_import(topopt_handle* h, const void* all, int64_t nbytes_each) {
   if (!h || !all) return fail(h, TOPOPT_ERR_INVALID, "topopt_ipc_import: NULL argument");
   if (h->world < 2 || h->world > kMaxRanks) return fail(h, TOPOPT_ERR_INVALID, "topopt_ipc_import: needs 2..8 ranks");
-  if (nbytes_each != (int64_t)(2 * sizeof(cudaIpcMemHandle_t) + sizeof(int32_t)) || !h->d_peerblock)
+  if (nbytes_each != (int64_t)(7 * sizeof(cudaIpcMemHandle_t) + sizeof(int32_t)) || !h->d_peerblock)
     return fail(h, TOPOPT_ERR_INVALID, "topopt_ipc_import: call topopt_ipc_export first / bad blob size");
   TRY(use_device(h));
   PeerComm pc;
@@ -1028,7 +1046,7 @@ int topopt_ipc_import(topopt_handle* h, const void* all, int64_t nbytes_each) {
     int32_t nown = 0;
     std::memcpy(&hb, blob, sizeof(hb));
     std::memcpy(&hp, blob + sizeof(hb), sizeof(hp));
-    std::memcpy(&nown, blob + 2 * sizeof(hb), sizeof(nown));
+    std::memcpy(&nown, blob + 7 * sizeof(hb), sizeof(nown));
     if (r == h->rank) {
       pc.block[r] = h->d_peerblock;
       continue;
@@ -1041,17 +1059,28 @@ int topopt_ipc_import(topopt_handle* h, const void* all, int64_t nbytes_each) {
       void* mp = nullptr;
       CUDA_TRY(h, cudaIpcOpenMemHandle(&mp, hp, cudaIpcMemLazyEnablePeerAccess));
       h->peer_mapped[kMaxRanks + r] = mp;
-      if (r == h->rank - 1) {
+      const int side = r == h->rank - 1 ? 0 : 1;
+      if (side == 0) {
         h->peer_p_lo = static_cast<const double*>(mp);
         h->nown_lower = nown;
       } else {
         h->peer_p_hi = static_cast<const double*>(mp);
+      }
+      (side == 0 ? h->peer_lo : h->peer_hi)[0] = static_cast<const double*>(mp);
+      for (int k = 1; k < 6; ++k) {
+        cudaIpcMemHandle_t hv;
+        std::memcpy(&hv, blob + (1 + k) * sizeof(hb), sizeof(hv));
+        void* mv = nullptr;
+        CUDA_TRY(h, cudaIpcOpenMemHandle(&mv, hv, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_mapped_vec[side][k] = mv;
+        (side == 0 ? h->peer_lo : h->peer_hi)[k] = static_cast<const double*>(mv);
       }
     }
   }
   if (!h->d_peercomm) CUDA_TRY(h, cudaMalloc((void**)&h->d_peercomm, sizeof(PeerComm)));
   CUDA_TRY(h, cudaMemcpy(h->d_peercomm, &pc, sizeof(pc), cudaMemcpyHostToDevice));
   h->peer_ready = !getenv("TOPOPT_NO_PEER");
+  h->peer_fused_ready = h->peer_ready;
   return TOPOPT_OK;
 }
 
@@ -1188,6 +1217,7 @@ int topopt_create(const topopt_desc* d, topopt_handle** out) {
     if (const char* e = getenv("TOPOPT_CG_FUSED")) h->cg_fused = atoi(e);
     if (const char* e = getenv("TOPOPT_CG_FUSED_GRID")) h->cg_fused_grid = std::max(1, atoi(e));
     if (const char* e = getenv("TOPOPT_KXU_GRID")) h->kxu_grid = std::max(1, atoi(e));
+    if (const char* e = getenv("TOPOPT_CG_FUSED_MGPU")) h->cg_fused_single_only = atoi(e) == 0;
   }
   if (const char* e = getenv("TOPOPT_CG_VARIANT")) h->cg_variant_env = atoi(e);
 
@@ -1345,6 +1375,9 @@ int topopt_destroy(topopt_handle* h) {
   h->mg = nullptr;
   for (void* m : h->peer_mapped)
     if (m) cudaIpcCloseMemHandle(m);
+  for (int side = 0; side < 2; ++side)
+    for (void* m : h->peer_mapped_vec[side])
+      if (m) cudaIpcCloseMemHandle(m);
   if (h->d_peerblock) cudaFree(h->d_peerblock);
   if (h->d_peercomm) cudaFree(h->d_peercomm);
   void* ptrs[] = {h->d_block, h->d_fixed, h->d_b, h->d_fload, h->d_u, h->d_r, h->d_p, h->d_p2, h->d_Ap, h->d_r2, h->d_Ap2, h->d_D, h->d_rhs, h->d_lam,

@@ -42,9 +42,18 @@ struct CGFusedVecs {
   double* r[2];
   double* ap[2];
   double* x;
+  // multi-GPU (PEER): the slab neighbours' boundary planes of the same six buffers, [p, r, Ap][parity], mapped over
+  // cudaIpc; lo = the lower neighbour's top owned plane (this rank's ghost plane 0), hi = the upper neighbour's first
+  // owned plane (ghost plane nown + 1).  NULL at the ends of the slab stack.
+  const double* lo[3][2];
+  const double* hi[3][2];
 };
 
-template <int TYT, int NST, bool CUBE>
+// PEER: the ghost planes are bulk-copied straight from the neighbours' memory once their previous kernel (iteration
+// k - 1: all of p, r, Ap final, scalars all-reduced) has signalled; this kernel signals in turn from its last CTA.  The
+// ping-pong parity keeps a neighbour that is one kernel ahead from overwriting what is still being read: it cannot
+// start iteration k + 1 before this rank has posted its sums of iteration k, which it does after its last read.
+template <int TYT, int NST, bool CUBE, bool PEER>
 __global__ void __launch_bounds__(32 * (TYT + 1), 1)
     k_cg_fused_hex8(Geo g, CGFusedVecs vec, const double* __restrict__ E, const unsigned char* __restrict__ fixed, double fixed_diag,
                     int tilesX, int tilesY, double* partials, CGState* st, int fin) {
@@ -108,6 +117,8 @@ __global__ void __launch_bounds__(32 * (TYT + 1), 1)
       long long su0;
       long long idx;
       const double* src;
+      const double* glo;  // PEER: source of ghost plane 0 / nown + 1 (NULL: local)
+      const double* ghi;
       int P, last;
       int dst, dst_stride, w, k, clip;
       unsigned fcount;
@@ -131,6 +142,8 @@ __global__ void __launch_bounds__(32 * (TYT + 1), 1)
         J.k = 2;
       }
       J.src = v == 0 ? pin : (v == 1 ? rin : apin);
+      J.glo = PEER ? vec.lo[v][parity] : nullptr;
+      J.ghi = PEER ? vec.hi[v][parity] : nullptr;
       J.stg = v != 0;
       // destination of stage 0 and the distance between stages (the staging area reuses slot `stage & 1`)
       if (v == 0) {
@@ -153,6 +166,7 @@ __global__ void __launch_bounds__(32 * (TYT + 1), 1)
       J.clip = 0;
     }
     bool alldone;
+    long long halo_spins = 0;
     do {
       bool progressed = false;
       alldone = true;
@@ -182,12 +196,32 @@ __global__ void __launch_bounds__(32 * (TYT + 1), 1)
         }
         alldone = false;
         const int sidx = (int)(J.fcount % NST);
-        const bool ready = J.stg ? (J.fcount < 2 || mbar_test_wait(&sempty[J.w][J.fcount & 1u], ((J.fcount >> 1) + 1u) & 1u))
-                                 : (J.fcount < NST || mbar_test_wait(&empty[J.w][sidx], ((J.fcount / NST) + 1u) & 1u));
+        bool ready = J.stg ? (J.fcount < 2 || mbar_test_wait(&sempty[J.w][J.fcount & 1u], ((J.fcount >> 1) + 1u) & 1u))
+                           : (J.fcount < NST || mbar_test_wait(&empty[J.w][sidx], ((J.fcount / NST) + 1u) & 1u));
+        const char* plane = reinterpret_cast<const char*>(J.src + (long long)J.P * g.S * 3);
+        if (PEER) {
+          const bool glo = J.glo != nullptr && J.P == 0, ghi = J.ghi != nullptr && J.P == g.nown + 1;
+          if (glo || ghi) {
+            PeerComm* pc = st->peer;
+            const volatile unsigned long long* f = pc->block[pc->rank]->halo_flag;
+            if (f[glo ? 0 : 1] < pc->halo_seq) {
+              if (++halo_spins > kSpinLimit / 8) {
+                pc->timeout = 1;  // a dead peer must not hang the GPU: proceed, the solve reports the error
+              } else {
+                ready = false;
+              }
+            }
+            plane = reinterpret_cast<const char*>(glo ? J.glo : J.ghi);
+            if (ready) {
+              __threadfence_system();
+              asm volatile("fence.proxy.async;" ::: "memory");
+            }
+          }
+        }
         if (ready) {
           uint64_t* bar = &full[J.w][sidx];
           if (J.ok) {
-            const char* a = reinterpret_cast<const char*>(J.src + (long long)J.P * g.S * 3) + J.idx;
+            const char* a = plane + J.idx;
             const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(a) & 15);
             const uint32_t nb = (lead + J.bytes + 15u) & ~15u;
             const int slot = J.dst_stride == kRingStage ? sidx : (sidx & 1);
@@ -242,7 +276,12 @@ __global__ void __launch_bounds__(32 * (TYT + 1), 1)
       const unsigned leadN0 = (unsigned)(((long long)r0 * g.NX + c_lo) & 1) << 3;
       const unsigned leadNB = leadN0 ^ ((unsigned)(g.NX & 1) << 3);
       auto plane_lead = [&](int P) -> unsigned {
-        return (unsigned)(reinterpret_cast<uintptr_t>(pin + (long long)P * g.S * 3) & 8);
+        const double* pp = pin + (long long)P * g.S * 3;
+        if (PEER) {  // p, r and Ap of a neighbour share their 16-byte alignment (separate cudaMalloc allocations)
+          if (vec.lo[0][parity] != nullptr && P == 0) pp = vec.lo[0][parity];
+          if (vec.hi[0][parity] != nullptr && P == g.nown + 1) pp = vec.hi[0][parity];
+        }
+        return (unsigned)(reinterpret_cast<uintptr_t>(pp) & 8);
       };
       // ---- combine bookkeeping: lane tx handles the flat values v = tx + 32 j (v = 3 node + comp) of a 33-node row
       unsigned vmask = 0, omask = 0;  // bit j: value in the domain / value of a node this tile owns (columns 1..31)
@@ -539,7 +578,7 @@ __global__ void __launch_bounds__(32 * (TYT + 1), 1)
       sf = s_new;
     }  // segments
   }
-  block_partials_finish<3>(dots, partials, st, fin, sm);
+  block_partials_finish<3>(dots, partials, st, fin, sm, PEER);
 }
 
 }  // namespace topopt

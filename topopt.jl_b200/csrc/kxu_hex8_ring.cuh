@@ -601,7 +601,8 @@ __global__ void __launch_bounds__(32 * (TYT + 1), (TYT <= 5 ? 2 : 1))
       sf = s_new;
     }  // segments
   }
-  if (DOT) block_partials_finish<NS>(dots, partials, st, fin, sm);
+  // fin & 0x100: also tell the slab neighbours that this rank's product is final (first K.p of the one-kernel CG loop)
+  if (DOT) block_partials_finish<NS>(dots, partials, st, fin & 0xff, sm, PEER && (fin & 0x100) != 0);
 }
 
 }  // namespace topopt

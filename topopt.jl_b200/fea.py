@@ -153,7 +153,7 @@ class GenericFEASolver:
         _lib.check(self._lib.topopt_create(C.byref(d), C.byref(self._handle)))
         if comm is not None and world > 1 and getattr(comm, "peer_memory", True):
             # peer-memory fast path: exchange cudaIpc handles (collective over all ranks)
-            buf = C.create_string_buffer(256)
+            buf = C.create_string_buffer(1024)
             n = C.c_int64()
             self._check(self._lib.topopt_ipc_export(self._handle, C.cast(buf, C.c_void_p), C.byref(n)))
             blobs = comm.all_gather_bytes(buf.raw[: n.value])
