@@ -198,12 +198,14 @@ def test_one_kernel_cg_iteration_matches_two_kernel_single_pass(lib, nels, monke
     b.close()
 
 
+@pytest.mark.parametrize("tma", ["0", "1"])
 @pytest.mark.parametrize("nels,grid", [((70, 44, 24), "0"), ((70, 44, 24), "7"), ((70, 44, 24), "37"), ((40, 26, 50), "29"),
                                        ((70, 44, 24), "3"), ((70, 44, 24), "11"), ((40, 26, 50), "5"), ((256, 128, 128), "0")])
-def test_one_kernel_cg_iteration_dense_rhs(lib, nels, grid, monkeypatch):
+def test_one_kernel_cg_iteration_dense_rhs(lib, nels, grid, tma, monkeypatch):
     """A DENSE right-hand side makes every owned dof, every tile halo and every segment boundary of the one-kernel
     iteration live from the first iteration on (a point load only reaches them after many iterations).  Odd CTA counts
-    (TOPOPT_CG_FUSED_GRID) put segment boundaries inside tile columns and across them.  Against the two-kernel path:
+    (TOPOPT_CG_FUSED_GRID) put segment boundaries inside tile columns and across them; both staging variants (row-wise
+    bulk copies, tensor-map boxes).  Against the two-kernel path:
     iterates <= 1e-12, residual norms <= 1e-11; the 3-iterate also against the oracle / the C port."""
     t = lib
     if nels[0] == 256 and os.environ.get("TOPOPT_SKIP_FULL_SIZE") == "1":
@@ -215,6 +217,7 @@ def test_one_kernel_cg_iteration_dense_rhs(lib, nels, grid, monkeypatch):
 
     def mk(fused, maxiter):
         monkeypatch.setenv("TOPOPT_CG_FUSED", "1" if fused else "0")
+        monkeypatch.setenv("TOPOPT_CG_FUSED_TMA", tma)  # 1: planes staged by tensor-map copies (kxu_hex8_cgtma.cuh)
         if grid != "0":
             monkeypatch.setenv("TOPOPT_CG_FUSED_GRID", grid)
         return t.FEASolver(t.CUDAMatrixFreeSolver, prob, penalty=t.PowerPenaltyFun(3.0), cg_variant=1, cg_max_iter=maxiter, abstol=0.0, reltol=0.0)

@@ -15,6 +15,8 @@ DEPS = SOURCES + [
     os.path.join(HERE, "csrc", "kxu_hex8_2row.cuh"),
     os.path.join(HERE, "csrc", "kxu_hex8_ring.cuh"),
     os.path.join(HERE, "csrc", "kxu_hex8_cgfused.cuh"),
+    os.path.join(HERE, "csrc", "kxu_hex8_cgtma.cuh"),
+    os.path.join(HERE, "csrc", "mg_solve.inl"),
     os.path.join(HERE, "csrc", "multigrid.cuh"),
     os.path.join(HERE, "csrc", "common.h"),
     os.path.join(ROOT, "include", "topopt_cuda.h"),

@@ -21,6 +21,7 @@
 #include "kxu_hex8_2row.cuh"
 #include "kxu_hex8_ring.cuh"
 #include "kxu_hex8_cgfused.cuh"
+#include "kxu_hex8_cgtma.cuh"
 #include "multigrid.cuh"
 
 using namespace topopt;
@@ -127,6 +128,9 @@ struct topopt_handle {
   const double* peer_hi[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   void* peer_mapped_vec[2][6] = {{nullptr}};
   bool peer_fused_ready = false;
+  CUtensorMap* d_tmaps = nullptr;  // tensor maps of the CG vectors (kxu_hex8_cgtma.cuh), built at the first one-kernel iteration
+  int tmaps_rows = 0;              // thread rows the maps' boxes were built for
+  int cg_fused_tma = 0;            // 1: stage planes with tensor-map copies (kxu_hex8_cgtma.cuh; 219 us vs 202 us at config 4), 0: row-wise bulk copies
   const double* peer_p_lo = nullptr;   // lower neighbour's d_p (mapped)
   const double* peer_p_hi = nullptr;   // upper neighbour's d_p (mapped)
   bool peer_ready = false;
@@ -548,20 +552,117 @@ int launch_cg_fused_t(topopt_handle* h, int fin) {
   if (h->modal_cube && h->kxu_cube) {
     static std::atomic<unsigned long long> attr_mask{0};
     TRY(ensure_dyn_smem(h, k_cg_fused_hex8<TYT, NST, true, PEER>, smem, attr_mask));
-    k_cg_fused_hex8<TYT, NST, true, PEER><<<grid, 32 * (TYT + 1), smem, h->stream>>>(g, v, h->d_E, h->d_fixed, h->fixed_diag, tilesX,
+    k_cg_fused_hex8<TYT, NST, true, PEER><<<grid, 32 * (TYT + kFusedProducers), smem, h->stream>>>(g, v, h->d_E, h->d_fixed, h->fixed_diag, tilesX,
                                                                                    tilesY, h->d_partials, h->d_st, fin);
   } else {
     static std::atomic<unsigned long long> attr_mask{0};
     TRY(ensure_dyn_smem(h, k_cg_fused_hex8<TYT, NST, false, PEER>, smem, attr_mask));
-    k_cg_fused_hex8<TYT, NST, false, PEER><<<grid, 32 * (TYT + 1), smem, h->stream>>>(g, v, h->d_E, h->d_fixed, h->fixed_diag, tilesX,
+    k_cg_fused_hex8<TYT, NST, false, PEER><<<grid, 32 * (TYT + kFusedProducers), smem, h->stream>>>(g, v, h->d_E, h->d_fixed, h->fixed_diag, tilesX,
                                                                                     tilesY, h->d_partials, h->d_st, fin);
   }
   h->stats.kernel_launches += 1;
   return check_launch(h, "k_cg_fused_hex8");
 }
 
+// ---- tensor maps of the six CG vectors (and the slab neighbours') for kxu_hex8_cgtma.cuh ----
+typedef CUresult (*PFN_tmap_encode_tiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                          const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                          CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int ensure_tmaps(topopt_handle* h, int tyt) {
+  if (h->d_tmaps && h->tmaps_rows == tyt) return TOPOPT_OK;
+  static PFN_tmap_encode_tiled encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr ||
+        qres != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return fail(h, TOPOPT_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    }
+    encode = reinterpret_cast<PFN_tmap_encode_tiled>(fn);
+  }
+  const Geo& g = h->g;
+  const int shift = (g.NX & 1) ? 1 : 0;
+  const long long row_doubles = (long long)g.NX * 3;
+  std::vector<CUtensorMap> maps(36);
+  std::memset(maps.data(), 0, sizeof(CUtensorMap) * maps.size());
+  // even / odd rows of the [R = plane * NY + row][3 NX] view of one vector with `planes` node planes
+  auto build = [&](const double* base, long long planes, CUtensorMap* out) -> int {
+    const long long Rtot = planes * g.NY;
+    for (int q = 0; q < 2; ++q) {
+      const long long rows = q == 0 ? (Rtot + 1) / 2 : Rtot / 2;
+      const double* b = q == 0 ? base : base + row_doubles - shift;
+      const cuuint64_t gdim[2] = {(cuuint64_t)(row_doubles + (q == 1 ? shift : 0)), (cuuint64_t)std::max<long long>(rows, 1)};
+      const cuuint64_t gstride[1] = {(cuuint64_t)(2 * row_doubles * 8)};
+      const cuuint32_t box[2] = {100u, (cuuint32_t)(tyt + 1)};
+      const cuuint32_t estr[2] = {1u, 1u};
+      const CUresult r = encode(&out[q], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(b), gdim, gstride, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(h, TOPOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+    }
+    return TOPOPT_OK;
+  };
+  const double* own[6] = {h->d_p, h->d_p2, h->d_r, h->d_r2, h->d_Ap, h->d_Ap2};
+  for (int b = 0; b < 6; ++b) {
+    TRY(build(own[b], g.nown + 2, &maps[2 * b]));
+    // neighbours: only their boundary plane is read; their buffers hold at least nown_lower + 2 / 3 planes
+    if (h->peer_lo[b]) TRY(build(h->peer_lo[b], h->nown_lower + 2, &maps[12 + 2 * b]));
+    if (h->peer_hi[b]) TRY(build(h->peer_hi[b], 3, &maps[24 + 2 * b]));
+  }
+  if (!h->d_tmaps) CUDA_TRY(h, cudaMalloc((void**)&h->d_tmaps, sizeof(CUtensorMap) * maps.size()));
+  CUDA_TRY(h, cudaMemcpy(h->d_tmaps, maps.data(), sizeof(CUtensorMap) * maps.size(), cudaMemcpyHostToDevice));
+  h->tmaps_rows = tyt;
+  return TOPOPT_OK;
+}
+
+template <int TYT, bool PEER>
+int launch_cg_tma_t(topopt_handle* h, int fin) {
+  constexpr int NST = 4;
+  const Geo& g = h->g;
+  constexpr int OWNR = 2 * TYT - 1;
+  const int tilesX = (g.NX + 30) / 31, tilesY = (g.NY + OWNR - 1) / OWNR;
+  const long long units = (long long)tilesX * tilesY * g.nown;
+  int grid = h->cg_fused_grid > 0 ? h->cg_fused_grid : aligned_grid(tilesX * tilesY, g.nown);
+  if (units < grid) grid = (int)units;
+  const size_t smem = hex8_cgtma_smem(TYT, NST);
+  TRY(ensure_tmaps(h, TYT));
+  CGFusedVecs v;
+  std::memset(&v, 0, sizeof(v));
+  v.p[0] = h->d_p;
+  v.p[1] = h->d_p2;
+  v.r[0] = h->d_r;
+  v.r[1] = h->d_r2;
+  v.ap[0] = h->d_Ap;
+  v.ap[1] = h->d_Ap2;
+  v.x = h->d_u;
+  CGTmaArgs ta;
+  ta.maps = h->d_tmaps;
+  ta.shift = (g.NX & 1) ? 1 : 0;
+  ta.lo_plane = (PEER && h->peer_lo[0]) ? h->nown_lower : -1;
+  ta.hi_plane = (PEER && h->peer_hi[0]) ? 1 : -1;
+  if (h->modal_cube && h->kxu_cube) {
+    static std::atomic<unsigned long long> attr_mask{0};
+    TRY(ensure_dyn_smem(h, k_cg_tma_hex8<TYT, NST, true, PEER>, smem, attr_mask));
+    k_cg_tma_hex8<TYT, NST, true, PEER><<<grid, 32 * (TYT + 1), smem, h->stream>>>(g, v, ta, h->d_E, h->d_fixed, h->fixed_diag, tilesX,
+                                                                                 tilesY, h->d_partials, h->d_st, fin);
+  } else {
+    static std::atomic<unsigned long long> attr_mask{0};
+    TRY(ensure_dyn_smem(h, k_cg_tma_hex8<TYT, NST, false, PEER>, smem, attr_mask));
+    k_cg_tma_hex8<TYT, NST, false, PEER><<<grid, 32 * (TYT + 1), smem, h->stream>>>(g, v, ta, h->d_E, h->d_fixed, h->fixed_diag, tilesX,
+                                                                                  tilesY, h->d_partials, h->d_st, fin);
+  }
+  h->stats.kernel_launches += 1;
+  return check_launch(h, "k_cg_tma_hex8");
+}
+
 int launch_cg_fused(topopt_handle* h, bool peer, int fin) {
   const int rows = fused_rows(h);
+  if (h->cg_fused_tma) {
+    if (peer) return rows == 8 ? launch_cg_tma_t<8, true>(h, fin) : launch_cg_tma_t<10, true>(h, fin);
+    return rows == 8 ? launch_cg_tma_t<8, false>(h, fin) : launch_cg_tma_t<10, false>(h, fin);
+  }
   if (peer) return rows == 8 ? launch_cg_fused_t<8, true>(h, fin) : launch_cg_fused_t<10, true>(h, fin);
   return rows == 8 ? launch_cg_fused_t<8, false>(h, fin) : launch_cg_fused_t<10, false>(h, fin);
 }
@@ -805,7 +906,7 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
         mix((unsigned long long)(uintptr_t)q);
       mix((unsigned long long)n);
       mix((unsigned long long)(energy ? 1 : 0) | (assembled ? 2 : 0) | (peer_halo ? 4 : 0) | (peer ? 8 : 0) | (single ? 16 : 0) |
-          (use_ring(h) ? 32 : 0) | (fused ? 64 : 0) | ((unsigned long long)ring_rows(h) << 8) | ((unsigned long long)(fused ? fused_rows(h) : 0) << 16));
+          (use_ring(h) ? 32 : 0) | (fused ? 64 : 0) | (h->cg_fused_tma ? 128 : 0) | ((unsigned long long)ring_rows(h) << 8) | ((unsigned long long)(fused ? fused_rows(h) : 0) << 16));
       if (h->cg_graph == nullptr || h->cg_graph_key != key) {
         if (h->cg_graph) {
           cudaGraphExecDestroy(h->cg_graph);
@@ -1218,6 +1319,7 @@ int topopt_create(const topopt_desc* d, topopt_handle** out) {
     if (const char* e = getenv("TOPOPT_CG_FUSED_GRID")) h->cg_fused_grid = std::max(1, atoi(e));
     if (const char* e = getenv("TOPOPT_KXU_GRID")) h->kxu_grid = std::max(1, atoi(e));
     if (const char* e = getenv("TOPOPT_CG_FUSED_MGPU")) h->cg_fused_single_only = atoi(e) == 0;
+    if (const char* e = getenv("TOPOPT_CG_FUSED_TMA")) h->cg_fused_tma = atoi(e);
   }
   if (const char* e = getenv("TOPOPT_CG_VARIANT")) h->cg_variant_env = atoi(e);
 
@@ -1373,6 +1475,7 @@ int topopt_destroy(topopt_handle* h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   mg_free(h->mg);
   h->mg = nullptr;
+  if (h->d_tmaps) cudaFree(h->d_tmaps);
   for (void* m : h->peer_mapped)
     if (m) cudaIpcCloseMemHandle(m);
   for (int side = 0; side < 2; ++side)

@@ -30,6 +30,8 @@
 
 namespace topopt {
 
+constexpr int kFusedProducers = 2;  // producer warps: every bulk copy costs ~50 cycles of its issuing warp (one lane at a time
+                                    // through the uniform datapath), 63 copies per plane -- a single producer is the bottleneck
 constexpr int kFusedStageRows = 8;  // staging rows per compute warp: 2 stages x {r, Ap} x rows {A, B}
 
 __host__ __device__ constexpr size_t hex8_fused_smem(int tyt, int nst) {
@@ -54,7 +56,7 @@ struct CGFusedVecs {
 // ping-pong parity keeps a neighbour that is one kernel ahead from overwriting what is still being read: it cannot
 // start iteration k + 1 before this rank has posted its sums of iteration k, which it does after its last read.
 template <int TYT, int NST, bool CUBE, bool PEER>
-__global__ void __launch_bounds__(32 * (TYT + 1), 1)
+__global__ void __launch_bounds__(32 * (TYT + kFusedProducers), 1)
     k_cg_fused_hex8(Geo g, CGFusedVecs vec, const double* __restrict__ E, const unsigned char* __restrict__ fixed, double fixed_diag,
                     int tilesX, int tilesY, double* partials, CGState* st, int fin) {
   static_assert(NST % 2 == 0, "the staging area is two deep: its slot is the ring stage modulo 2");
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(32 * (TYT + 1), 1)
   double* __restrict__ xsol = vec.x;
   const int tid = threadIdx.x;
   const int tx = tid & 31, wid = tid >> 5;
-  const bool producer = wid == TYT;
+  const bool producer = wid >= TYT;
   const int ty = producer ? 0 : TYT - 1 - wid;
   const unsigned FULL = 0xffffffffu;
   if (tid < TYT * NST) {
@@ -98,8 +100,8 @@ __global__ void __launch_bounds__(32 * (TYT + 1), 1)
   }
   if (tid < TYT) sflag[tid] = cflag[tid] = 0;
   if (tid < 4) zero3[tid] = 0.0;
-  for (int i = tid; i < YB0 / 16; i += 32 * (TYT + 1)) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < 2 * 6 * (TYT + 1) * 32; i += 32 * (TYT + 1)) (&yb[0][0][0][0])[i] = 0.0;
+  for (int i = tid; i < YB0 / 16; i += (int)blockDim.x) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 2 * 6 * (TYT + 1) * 32; i += (int)blockDim.x) (&yb[0][0][0][0])[i] = 0.0;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
 
@@ -112,7 +114,9 @@ __global__ void __launch_bounds__(32 * (TYT + 1), 1)
     // =========================== producer warp ===========================
     // job j < 6 TYT: thread row j / 6, vector (j % 6) / 2 in {p, r, Ap}, row (j % 2) in {A, B}; the last three jobs are
     // row C of the top thread row (its upper neighbour belongs to another tile).
-    constexpr int NJ = 6 * TYT + 3, JPL = (NJ + 31) / 32;
+    // the jobs are dealt round-robin to the producer warps
+    constexpr int NJ = 6 * TYT + 3, JPL = (NJ + 32 * kFusedProducers - 1) / (32 * kFusedProducers);
+    const int pw = wid - TYT;
     struct Job {
       long long su0;
       long long idx;
@@ -127,7 +131,7 @@ __global__ void __launch_bounds__(32 * (TYT + 1), 1)
     } job[JPL];
 #pragma unroll
     for (int q = 0; q < JPL; ++q) {
-      const int j = tx + 32 * q;
+      const int j = pw + kFusedProducers * (tx + 32 * q);
       Job& J = job[q];
       J.valid = j < NJ;
       J.done = !J.valid;
@@ -226,7 +230,15 @@ __global__ void __launch_bounds__(32 * (TYT + 1), 1)
             const uint32_t nb = (lead + J.bytes + 15u) & ~15u;
             const int slot = J.dst_stride == kRingStage ? sidx : (sidx & 1);
             mbar_arrive_expect_tx(bar, nb);
+#ifdef TOPOPT_EXPERIMENT_SPLIT_COPIES  // diagnostic: twice the bulk-copy requests for the same bytes
+            {
+              const uint32_t h1 = (nb / 2) & ~15u;
+              bulk_g2s(smem_raw + J.dst + slot * J.dst_stride + J.clip, a - lead, h1, bar);
+              bulk_g2s(smem_raw + J.dst + slot * J.dst_stride + J.clip + h1, a - lead + h1, nb - h1, bar);
+            }
+#else
             bulk_g2s(smem_raw + J.dst + slot * J.dst_stride + J.clip, a - lead, nb, bar);
+#endif
           } else {
             mbar_arrive(bar);
           }
