@@ -1,4 +1,9 @@
-timeout 900 python tools/r02_probe_fused.py 256,128,16 TOPOPT_CG_FUSED=1 TOPOPT_CG_FUSED_GRID=63 TOPOPT_CG_FUSED_GRID=126 TOPOPT_CG_FUSED_GRID=148 TOPOPT_CG_FUSED_GRID=189 TOPOPT_CG_FUSED_GRID=252 TOPOPT_CG_FUSED_GRID=296 TOPOPT_CG_FUSED=8,TOPOPT_CG_FUSED_GRID=144 TOPOPT_CG_FUSED=8,TOPOPT_CG_FUSED_GRID=216 TOPOPT_CG_FUSED=0 > gpurun_out/r02_thin_p1.log 2>&1
-cat gpurun_out/r02_thin_p1.log
-timeout 900 python tools/r02_probe_fused.py 256,128,32 TOPOPT_CG_FUSED=1 TOPOPT_CG_FUSED_GRID=126 TOPOPT_CG_FUSED_GRID=148 TOPOPT_CG_FUSED_GRID=252 TOPOPT_CG_FUSED_GRID=189 TOPOPT_CG_FUSED=0 > gpurun_out/r02_thin_p2.log 2>&1
-cat gpurun_out/r02_thin_p2.log
+timeout 2400 python -m pytest tests -x -q -m gpu 2>&1 | tail -8 > gpurun_out/r02_gputest3.log
+cat gpurun_out/r02_gputest3.log
+timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/r02_bench_n1_e.json 2> gpurun_out/r02_bench_n1_e.err
+python -c "
+import json
+d=json.load(open('gpurun_out/r02_bench_n1_e.json'))
+print(d['value'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['ms_per_launch'], d['kxu_alone']['ms_per_launch'], d['clocks'], d['multigrid_run']['step_s'], d['cpu_baseline']['value'])
+"
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
