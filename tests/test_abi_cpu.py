@@ -244,3 +244,30 @@ def test_header_is_plain_c_and_links(tmp_path):
     assert res.returncode == 0, res.stderr
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
     assert out == ["0", "45", "16", "135", "5733"]
+
+
+def test_save_mesh_vtu_like_the_reference(tmp_path):
+    """save_mesh (src/TopOptProblems/IO/VTK.jl:33-62): cells with density >= 0.5 only, every node, Ferrite local node
+    order; a wrong-length density vector raises like the reference's ArgumentError.  Host-only (no GPU)."""
+    import base64
+    import re
+
+    import topopt_jl_b200 as t
+
+    prob = t.PointLoadCantilever((4, 2, 2))
+    rho = np.linspace(0.0, 1.0, prob.nel)
+    (path,) = t.save_mesh(str(tmp_path / "design"), prob, rho)
+    xml = open(path).read()
+    assert f'NumberOfPoints="{prob.nnodes}"' in xml and f'NumberOfCells="{int((rho >= 0.5).sum())}"' in xml
+    blob = re.search(r'Name="connectivity" format="binary">([^<]*)<', xml).group(1)
+    raw = base64.b64decode(blob)
+    conn = np.frombuffer(raw[4:], dtype=np.int64).reshape(-1, 8)
+    assert np.array_equal(conn, prob.metadata.cells[rho >= 0.5] - 1)
+    dens = np.frombuffer(base64.b64decode(re.search(r'Name="density" format="binary">([^<]*)<', xml).group(1))[4:], dtype=np.float64)
+    assert np.array_equal(dens, rho[rho >= 0.5])
+    u = np.arange(prob.ndof, dtype=np.float64)
+    (path2,) = t.save_mesh(str(tmp_path / "with_u.vtu"), prob, rho, nodal=u)
+    disp = np.frombuffer(base64.b64decode(re.search(r'Name="displacement"[^>]*>([^<]*)<', open(path2).read()).group(1))[4:], dtype=np.float64)
+    assert np.array_equal(disp.reshape(-1, 3), u[prob.metadata.node_dofs.T - 1])
+    with pytest.raises(ValueError):
+        t.save_mesh(str(tmp_path / "bad"), prob, rho[:-1])

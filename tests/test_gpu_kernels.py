@@ -502,6 +502,13 @@ def test_device_resident_simp_loop(lib, nels, filt):
     xo, ho = o.simp_loop(oprob, 2.0, 0.4, p=3.0, xmin=1e-3, iters=10, filt=filt, abstol=1e-11, maxiter=20000)
     assert np.max(np.abs(xd - xo)) < 1e-6 and rel(hd, ho) < 1e-8
     assert abs(float(xd @ (prob.cellvolumes / prob.cellvolumes.sum())) - 0.4) < 1e-9 or filt == "density"
+    # VTK export straight from the device-resident design (VTK.jl:33-62): same cells as from the host copy
+    assert np.array_equal(t.device_design(s2), xd)
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        (fa,) = t.save_mesh(os.path.join(d, "dev"), prob, solver=s2, nodal=True)
+        (fb,) = t.save_mesh(os.path.join(d, "host"), prob, xd, nodal=s2.u)
+        assert open(fa).read() == open(fb).read() and f'NumberOfCells="{int((xd >= 0.5).sum())}"' in open(fa).read()
     # one update against the host rule on arbitrary inputs
     x = np.random.default_rng(1).uniform(0.05, 1.0, prob.nel)
     dc = -np.random.default_rng(2).uniform(0.0, 3.0, prob.nel)

@@ -19,6 +19,7 @@ from .fea import (
     SinhPenaltyFun,
     getcompliance,
 )
+from .io import device_design, save_mesh
 from .functions import ComplianceFun, DisplacementFun, TemperatureFun, ThermalComplianceFun, VolumeFun
 from .problems import HalfMBB, HeatConductionProblem, HeatTree, Metadata, PointLoadCantilever, element_matrix
 from .simp import oc_update, oc_update_device, simp_eval, simp_loop, simp_loop_device
