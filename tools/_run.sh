@@ -1,9 +1,7 @@
-timeout 2400 python -m pytest tests -x -q -m gpu 2>&1 | tail -8 > gpurun_out/r02_gputest3.log
-cat gpurun_out/r02_gputest3.log
-timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/r02_bench_n1_e.json 2> gpurun_out/r02_bench_n1_e.err
-python -c "
-import json
-d=json.load(open('gpurun_out/r02_bench_n1_e.json'))
-print(d['value'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['ms_per_launch'], d['kxu_alone']['ms_per_launch'], d['clocks'], d['multigrid_run']['step_s'], d['cpu_baseline']['value'])
-"
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+cp topopt.jl_b200/libtopopt_cuda.so /tmp/good.so
+for v in nst6 nosleep; do
+  cp tools/probes/variants/$v.so topopt.jl_b200/libtopopt_cuda.so
+  echo "== $v"
+  timeout 300 python tools/r02_probe_fused.py 256,128,128 TOPOPT_CG_FUSED_TMA=1 TOPOPT_CG_FUSED_TMA=0 2>&1 | tail -2
+done
+cp /tmp/good.so topopt.jl_b200/libtopopt_cuda.so

@@ -617,9 +617,12 @@ int ensure_tmaps(topopt_handle* h, int tyt) {
   return TOPOPT_OK;
 }
 
+#ifndef TOPOPT_TMA_NST
+#define TOPOPT_TMA_NST 4
+#endif
 template <int TYT, bool PEER>
 int launch_cg_tma_t(topopt_handle* h, int fin) {
-  constexpr int NST = 4;
+  constexpr int NST = TOPOPT_TMA_NST;
   const Geo& g = h->g;
   constexpr int OWNR = 2 * TYT - 1;
   const int tilesX = (g.NX + 30) / 31, tilesY = (g.NY + OWNR - 1) / OWNR;

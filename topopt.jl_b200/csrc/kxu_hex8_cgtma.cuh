@@ -58,8 +58,8 @@ __global__ void __launch_bounds__(32 * (TYT + 1), 1)
   constexpr int XS0 = S0 + 4 * PLANE;           // x_{k-1} of the next plane: [thread row][row A, B][j][lane]
   constexpr int YB0 = XS0 + TYT * 2 * 3 * 32 * 8;
   constexpr int OWNR = 2 * TYT - 1;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double(*yb)[6][TYT + 1][32] = reinterpret_cast<double(*)[6][TYT + 1][32]>(smem_raw + YB0);
+  extern __shared__ __align__(128) unsigned char smem_tma[];
+  double(*yb)[6][TYT + 1][32] = reinterpret_cast<double(*)[6][TYT + 1][32]>(smem_tma + YB0);
   // full: the plane's p and r / Ap have landed (two arrivals with byte counts); empty: ring stage released by every
   // thread row (tail); sempty: staging slot released by every thread row (combine)
   __shared__ uint64_t full[NST], empty[NST], sempty[2];
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(32 * (TYT + 1), 1)
   }
   if (tid < TYT) sflag[tid] = cflag[tid] = 0;
   if (tid < 4) zero3[tid] = 0.0;
-  for (int i = tid; i < YB0 / 16; i += (int)blockDim.x) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < YB0 / 16; i += (int)blockDim.x) reinterpret_cast<uint4*>(smem_tma)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < 2 * 6 * (TYT + 1) * 32; i += (int)blockDim.x) (&yb[0][0][0][0])[i] = 0.0;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(32 * (TYT + 1), 1)
           const int s = (int)(sp.f % NST);
           if ((sp.f < NST || mbar_test_wait(&empty[s], ((sp.f / NST) + 1u) & 1u)) && halo_ready(sp.P)) {
             mbar_arrive_expect_tx(&full[s], 2 * BOX);
-            issue(sp, 0, smem_raw + s * PLANE, &full[s]);
+            issue(sp, 0, smem_tma + s * PLANE, &full[s]);
             sp.P += 1;
             sp.f += 1;
             progressed = true;
@@ -183,14 +183,16 @@ __global__ void __launch_bounds__(32 * (TYT + 1), 1)
           const int s = (int)(ss.f % NST), slot = (int)(ss.f & 1u);
           if ((ss.f < 2 || mbar_test_wait(&sempty[slot], ((ss.f >> 1) + 1u) & 1u)) && halo_ready(ss.P)) {
             mbar_arrive_expect_tx(&full[s], 4 * BOX);
-            issue(ss, 1, smem_raw + S0 + slot * 2 * PLANE, &full[s]);
-            issue(ss, 2, smem_raw + S0 + slot * 2 * PLANE + PLANE, &full[s]);
+            issue(ss, 1, smem_tma + S0 + slot * 2 * PLANE, &full[s]);
+            issue(ss, 2, smem_tma + S0 + slot * 2 * PLANE + PLANE, &full[s]);
             ss.P += 1;
             ss.f += 1;
             progressed = true;
           }
         }
+#ifndef TOPOPT_TMA_NOSLEEP
         if (!progressed) __nanosleep(64);
+#endif
       }
     }
     __syncwarp();
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(32 * (TYT + 1), 1)
       };
       auto prefetch_l1 = [](const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); };
 
-      double(*xs)[3][32] = reinterpret_cast<double(*)[3][32]>(smem_raw + XS0 + ty * (2 * 3 * 32 * 8));
+      double(*xs)[3][32] = reinterpret_cast<double(*)[3][32]>(smem_tma + XS0 + ty * (2 * 3 * 32 * 8));
       auto issue_x = [&](int P) {
         const bool wr = P >= z0 && P < z1;
 #pragma unroll
@@ -294,8 +296,8 @@ __global__ void __launch_bounds__(32 * (TYT + 1), 1)
       auto combine = [&](int P, int s) {
         const bool wr = P >= z0 && P < z1;
         const int e0 = plane_e0(P);
-        unsigned char* pb = smem_raw + s * PLANE + 8 * tx;
-        const unsigned char* rb = smem_raw + S0 + (s & 1) * 2 * PLANE + 8 * tx;
+        unsigned char* pb = smem_tma + s * PLANE + 8 * tx;
+        const unsigned char* rb = smem_tma + S0 + (s & 1) * 2 * PLANE + 8 * tx;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           if (k == 2 && ty != TYT - 1) continue;
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(32 * (TYT + 1), 1)
         bool st_ok[2];
         unsigned char fl[2];
         {
-          const unsigned char* sb = smem_raw + s_tail * PLANE + 24 * tx;
+          const unsigned char* sb = smem_tma + s_tail * PLANE + 24 * tx;
 #pragma unroll
           for (int r = 0; r < 2; ++r) {
             st_ok[r] = store && own[r];
@@ -440,8 +442,8 @@ __global__ void __launch_bounds__(32 * (TYT + 1), 1)
         wait_rowC();
         RowX xr[3];
         {
-          const unsigned char* bb = smem_raw + s_old * PLANE + 24 * tx;
-          const unsigned char* bt = smem_raw + s_new * PLANE + 24 * tx;
+          const unsigned char* bb = smem_tma + s_old * PLANE + 24 * tx;
+          const unsigned char* bt = smem_tma + s_new * PLANE + 24 * tx;
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
             const double* qb = reinterpret_cast<const double*>(bb + row_off(e_old, k));
