@@ -150,10 +150,12 @@ int topopt_element_matrix(int32_t dim, int32_t physics, const double* sizes, dou
 int topopt_nccl_unique_id(void* out128);
 
 /* Peer-memory fast path for world > 1 (all ranks on one NVSwitch node, one process per GPU):
- * every rank exports a blob (cudaIpc handles of its communication block and direction vector),
- * the host all-gathers the blobs (any transport) and every rank imports all of them.  Afterwards
- * the CG loop all-reduces its scalars inside the reduction kernels and the K.u kernel reads halo
- * planes directly from the neighbours' memory over NVLink; without this call NCCL is used. */
+ * every rank exports a blob (cudaIpc handles of its communication block and its six CG vectors, 452 bytes;
+ * pass a buffer of >= 1024), the host all-gathers the blobs (any transport) and every rank imports all of
+ * them.  Afterwards the CG loop all-reduces its scalars inside its kernels and reads halo planes directly
+ * from the neighbours' memory over NVLink; without this call NCCL is used.  The path is all-or-nothing: if
+ * the import fails on ANY rank (no P2P), every rank must call topopt_ipc_import(h, NULL, 0), which unmaps
+ * whatever was mapped and returns the handle to the NCCL path. */
 int topopt_ipc_export(topopt_handle* h, void* out, int64_t* nbytes);
 int topopt_ipc_import(topopt_handle* h, const void* all_blobs, int64_t nbytes_each);
 

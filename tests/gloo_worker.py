@@ -34,6 +34,8 @@ def main():
     # equal-sized blobs must come back concatenated in rank order on every rank
     blob = bytes([rank]) * 452
     allb = comm.all_gather_bytes(blob)
+    # the all-or-nothing agreement on the peer path: false as soon as one rank could not import
+    assert comm.all_agree(True) is True and comm.all_agree(rank != 0) is False
     assert len(allb) == 452 * world and all(allb[452 * r:452 * (r + 1)] == bytes([r]) * 452 for r in range(world))
     for nels in ((6, 4, 5), (5, 7)):
         prob = o.PointLoadCantilever(nels) if len(nels) == 3 and nels[2] % 2 == 0 else o.HalfMBB(nels)

@@ -1133,12 +1133,38 @@ int topopt_ipc_export(topopt_handle* h, void* out, int64_t* nbytes) {
 }
 
 // import: the export blobs of all ranks, concatenated in rank order (every rank calls this)
+// unmap everything a previous import opened (idempotent)
+static void ipc_close_all(topopt_handle* h) {
+  for (void*& m : h->peer_mapped)
+    if (m) {
+      cudaIpcCloseMemHandle(m);
+      m = nullptr;
+    }
+  for (int side = 0; side < 2; ++side)
+    for (void*& m : h->peer_mapped_vec[side])
+      if (m) {
+        cudaIpcCloseMemHandle(m);
+        m = nullptr;
+      }
+  for (int k = 0; k < 6; ++k) h->peer_lo[k] = h->peer_hi[k] = nullptr;
+  h->peer_p_lo = h->peer_p_hi = nullptr;
+  h->peer_ready = h->peer_fused_ready = false;
+  cudaGetLastError();
+}
+
 int topopt_ipc_import(topopt_handle* h, const void* all, int64_t nbytes_each) {
-  if (!h || !all) return fail(h, TOPOPT_ERR_INVALID, "topopt_ipc_import: NULL argument");
+  if (!h) return fail(h, TOPOPT_ERR_INVALID, "topopt_ipc_import: NULL handle");
+  if (!all) {
+    // all == NULL: give the peer-memory path up (some rank could not map its neighbours): every rank then uses NCCL
+    TRY(use_device(h));
+    ipc_close_all(h);
+    return TOPOPT_OK;
+  }
   if (h->world < 2 || h->world > kMaxRanks) return fail(h, TOPOPT_ERR_INVALID, "topopt_ipc_import: needs 2..8 ranks");
   if (nbytes_each != (int64_t)(7 * sizeof(cudaIpcMemHandle_t) + sizeof(int32_t)) || !h->d_peerblock)
     return fail(h, TOPOPT_ERR_INVALID, "topopt_ipc_import: call topopt_ipc_export first / bad blob size");
   TRY(use_device(h));
+  ipc_close_all(h);  // a second import must not leak the first one's mappings
   PeerComm pc;
   std::memset(&pc, 0, sizeof(pc));
   pc.rank = h->rank;
@@ -1479,11 +1505,7 @@ int topopt_destroy(topopt_handle* h) {
   mg_free(h->mg);
   h->mg = nullptr;
   if (h->d_tmaps) cudaFree(h->d_tmaps);
-  for (void* m : h->peer_mapped)
-    if (m) cudaIpcCloseMemHandle(m);
-  for (int side = 0; side < 2; ++side)
-    for (void* m : h->peer_mapped_vec[side])
-      if (m) cudaIpcCloseMemHandle(m);
+  ipc_close_all(h);
   if (h->d_peerblock) cudaFree(h->d_peerblock);
   if (h->d_peercomm) cudaFree(h->d_peercomm);
   void* ptrs[] = {h->d_block, h->d_fixed, h->d_b, h->d_fload, h->d_u, h->d_r, h->d_p, h->d_p2, h->d_Ap, h->d_r2, h->d_Ap2, h->d_D, h->d_rhs, h->d_lam,

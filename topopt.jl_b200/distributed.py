@@ -43,6 +43,16 @@ class SlabComm:
         dist.all_gather(out, mine)
         return b"".join(bytes(t.cpu().tolist()) for t in out)
 
+    def all_agree(self, ok: bool) -> bool:
+        """True iff ``ok`` is true on every rank (collective)."""
+        import torch
+        import torch.distributed as dist
+
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(int(t.item()))
+
 
 def slab_ranges(nlayers, world):
     """element layers [e0, e1) and owned node planes [k0, k1) per rank (the upper rank owns a

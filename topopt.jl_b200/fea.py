@@ -157,7 +157,11 @@ class GenericFEASolver:
             n = C.c_int64()
             self._check(self._lib.topopt_ipc_export(self._handle, C.cast(buf, C.c_void_p), C.byref(n)))
             blobs = comm.all_gather_bytes(buf.raw[: n.value])
-            self._check(self._lib.topopt_ipc_import(self._handle, C.cast(C.c_char_p(blobs), C.c_void_p), n.value))
+            ok = self._lib.topopt_ipc_import(self._handle, C.cast(C.c_char_p(blobs), C.c_void_p), n.value) == _lib.OK
+            # the peer path is all-or-nothing: if one rank cannot map its neighbours (no P2P, ranks on different
+            # nodes) every rank falls back to the NCCL halo exchange / all-reduce instead of hanging in a collective
+            if not comm.all_agree(ok):
+                self._check(self._lib.topopt_ipc_import(self._handle, None, 0))
 
     # -- lifetime ------------------------------------------------------------------------------
     def close(self):
