@@ -488,6 +488,94 @@ def test_config5_heat_full_size(lib):
     S.close(); s.close()
 
 
+def test_config3_at_size_against_c_port(lib):
+    """BASELINE config 3 (60x20x20 hex8, 80 703 dofs) at full size against the C port of the reference CPU path:
+    port-CG to 1e-12, then compliance and sensitivities <= 1e-8, K.u <= 1e-12, filtered SIMP evaluation <= 1e-8."""
+    import ref_c
+
+    t = lib
+    nels = (60, 20, 20)
+    prob = t.PointLoadCantilever(nels)
+    R = ref_c.RefProblem(3, 3, nels, prob.Ke, prob.prescribed_dofs, openmp=True)
+    rho = rand_rho(prob.nel, 3)
+    R.set_density(rho, 3.0, 1e-6)
+    b = prob.fixedload.copy()
+    b[prob.prescribed_dofs - 1] = 0.0
+    uref, it, res = R.cg(b, abstol=1e-12, reltol=0.0, maxiter=100000)
+    assert res <= 1e-12
+    oref, cref, gref = R.compliance(uref, rho, 3.0, 1e-6)
+    s = make_solver(t, prob, xmin=1e-6, abstol=1e-12, reltol=0.0, cg_max_iter=100000)
+    comp = t.ComplianceFun(s)
+    v, g = comp.value_and_grad(rho)
+    assert s.last_result.converged == 1
+    assert abs(v - oref) / oref < RTOL_SOLVE and rel(g, gref) < RTOL_SOLVE and rel(s.u, uref) < 1e-7
+    x = np.random.default_rng(4).standard_normal(prob.ndof)
+    x[prob.prescribed_dofs - 1] = 0.0
+    assert rel(s.mul(x), R.mul(x)) < RTOL_OP
+    # the filtered evaluation of the tutorial loop (DensityFilter rmin = 2) against port filter + port solve
+    F = t.DensityFilterFun(s, 2.0)
+    gx = np.empty(prob.nel)
+    objf, _ = t.simp_eval(s, F, rho, gx)
+    xf = R.filter(2.0, rho)
+    R.set_density(xf, 3.0, 1e-6)
+    uf, _, resf = R.cg(b, abstol=1e-12, reltol=0.0, maxiter=100000)
+    of, _, gf = R.compliance(uf, xf, 3.0, 1e-6)
+    assert abs(objf - of) / of < RTOL_SOLVE
+    assert rel(F(rho), xf) < 1e-12
+    assert rel(gx, F.pullback(gf)) < RTOL_SOLVE  # the pullback itself is pinned against the oracle in test_filters
+    F.close(); s.close(); R.close()
+
+
+def test_config2_at_size_bit_exact_nzval(lib):
+    """BASELINE config 2 (HalfMBB 600x200, 241 602 dofs, 4 329 604 non-zeros) at full size: the assembled matrix is
+    bit-identical to the oracle's Ferrite-order assembly off the prescribed diagonal, the load vector bit-identical."""
+    t = lib
+    prob, oprob = t.HalfMBB((600, 200)), o.HalfMBB((600, 200))
+    prob.Ke = oprob.Ke.copy()
+    rho = rand_rho(prob.nel, 5)
+    E = o.get_rho(rho, 3.0, 1e-3)
+    s = t.FEASolver(t.CUDAAssemblySolver, prob, penalty=t.PowerPenaltyFun(3.0), abstol=1e-9, reltol=0.0, cg_max_iter=100000)
+    s._check(s._lib.topopt_set_stiffness(s.handle, E.ctypes.data, None))
+    nz, f = s.assemble()
+    cp, rv, nzref, fref = o.assemble(oprob, E)
+    colptr, rowval = prob.metadata.csc_pattern()
+    assert np.array_equal(colptr - 1, cp) and np.array_equal(rowval - 1, rv)
+    colidx = np.repeat(np.arange(oprob.ndof), np.diff(cp))
+    fixed_diag = (rv == colidx) & oprob.fixed_mask[rv]
+    assert np.array_equal(nz[~fixed_diag], nzref[~fixed_diag])
+    assert rel(nz[fixed_diag], nzref[fixed_diag]) < 1e-13
+    assert np.array_equal(f, fref)
+    s.close()
+
+
+def test_config5_at_size_against_c_port(lib):
+    """BASELINE config 5 (1024x1024 heat, 1 050 625 dofs) at full size, the C port as the checker: the GPU temperature
+    field satisfies the port's operator (|f - K_port T| <= 1e-7), and thermal compliance and sensitivities computed by the
+    port FROM that field match the GPU's <= 1e-10 (compute_thermal_compliance!, thermal_compliance.jl:116-158)."""
+    import ref_c
+
+    t = lib
+    nels = (1024, 1024)
+    prob = t.HeatTree(nels)
+    R = ref_c.RefProblem(2, 1, nels, prob.Ke, prob.prescribed_dofs, openmp=True)
+    rho = rand_rho(prob.nel, 6)
+    R.set_density(rho, 3.0, 1e-3)
+    s = make_solver(t, prob, abstol=1e-8, reltol=0.0, cg_max_iter=200000)
+    tc = t.ThermalComplianceFun(s)
+    J, g = tc.value_and_grad(rho)
+    assert s.last_result.converged == 1
+    T = s.u.copy()
+    b = prob.fixedload.copy()
+    b[prob.prescribed_dofs - 1] = 0.0
+    r = b - R.mul(T)
+    r[prob.prescribed_dofs - 1] = 0.0
+    assert np.linalg.norm(r) <= 1e-7
+    Jp, _, gp = R.compliance(T, rho, 3.0, 1e-3)  # T' K T and -dE T_e' Ke T_e: the same bilinear form as the thermal adjoint
+    assert abs(J - Jp) / Jp < 1e-7  # J = Q.T vs T'KT differ by the solve residual
+    assert rel(g, gp) < 1e-10
+    s.close(); R.close()
+
+
 @pytest.mark.parametrize("nels", [(64, 30, 18), (33, 8, 4), (31, 16, 4)])
 def test_hex8_modal_kernel_multi_tile_parity(lib, nels):
     """The modal K.u kernel tiles the grid in 30 x 14 node-column patches and marches persistent CTAs
