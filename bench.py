@@ -489,7 +489,7 @@ def run_small_config(args):
         name, prob, S, xmin, vf = workload_name(CFG3_NELS), t.PointLoadCantilever(CFG3_NELS), t.CUDAMatrixFreeSolver, XMIN, VOLFRAC
     else:
         name, prob, S, xmin, vf = "2D HeatConductionProblem 1024x1024 quad4 thermal compliance, SensFilter rmin=2, p=3", t.HeatTree((1024, 1024)), t.CUDAMatrixFreeSolver, 1e-3, 0.4
-    s = t.FEASolver(S, prob, penalty=t.PowerPenaltyFun(PENAL), xmin=xmin, abstol=1e-7, cg_max_iter=args.maxiter)
+    s = t.FEASolver(S, prob, penalty=t.PowerPenaltyFun(PENAL), xmin=xmin, abstol=1e-7, cg_max_iter=args.maxiter, cg_variant=args.cg_variant)
     x, g = np.full(prob.nel, vf), np.empty(prob.nel)
     if c == 5:
         F = t.SensFilterFun(s, RMIN)
@@ -519,7 +519,8 @@ def run_small_config(args):
     peak, peak_src = measured_peaks()
     assembled = c == 2
     kxu_ms = s.time_kernel(4 if assembled else 0, args.kernel_reps, F)
-    cg_ms = s.time_kernel(6 if assembled else 1, args.kernel_reps, F)
+    one_kernel = c == 3 and args.cg_variant == 1 and os.environ.get("TOPOPT_CG_FUSED", "1") != "0"  # hex8, >= 12 node planes
+    cg_ms = s.time_kernel(6 if assembled else (9 if one_kernel else 1), max(args.kernel_reps, 200) if one_kernel else args.kernel_reps, F)
     kbytes = (12 * md.nnz + 20 * md.ndof) if assembled else (16 * md.ndof + 8 * md.nel)
     line = {
         "metric": "simp_iterations_per_sec", "value": args.steps / wall, "unit": "it/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
@@ -533,7 +534,7 @@ def run_small_config(args):
         "roofline": {"kernel": "k_spmv (assembled CSR)" if assembled else "k_apply (matrix-free K.u)", "bound": "hbm", "achieved": kbytes / (kxu_ms * 1e-3) / 1e9,
                      "peak": peak, "unit": "GB/s", "frac": kbytes / (kxu_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": kbytes, "ms_per_launch": kxu_ms},
-        "cg_iteration": {"ms": cg_ms, "it_per_s": 1e3 / cg_ms},
+        "cg_iteration": {"ms": cg_ms, "it_per_s": 1e3 / cg_ms, "kernels_per_iteration": 1 if one_kernel else 3},
         "cpu_baseline": {"value": None, "unit": "it/s", "cores": 0, "kind": "port", "sample": "not timed for the secondary configs (see --config 4 and config3_full_step)"},
     }
     emit(line)
