@@ -265,6 +265,50 @@ def test_multigrid_preconditioned_cg(lib, nels):
     b.close()
 
 
+@pytest.mark.parametrize("kind,nels", [("cantilever", (40, 12)), ("cantilever", (10, 6, 8)), ("heat", (24, 24))])
+def test_persistent_cg_for_small_grids(lib, kind, nels, monkeypatch):
+    """k_cg_persistent: batches of CG iterations of the reference recurrence in ONE cooperative launch (three device-wide
+    barriers per iteration) on small grids.  Same iterates as the one-launch-per-kernel path and the oracle for
+    1 / 5 / 20 / 61 iterations (61 crosses a batch boundary), same stopping iteration, far fewer launches."""
+    t = lib
+    prob = t.PointLoadCantilever(nels) if kind == "cantilever" else t.HeatTree(nels)
+    oprob = o.PointLoadCantilever(nels) if kind == "cantilever" else o.HeatTree(nels)
+    prob.Ke = oprob.Ke.copy()
+    rho = rand_rho(prob.nel, 8)
+    E = o.get_rho(rho, 3.0, 1e-3)
+
+    def mk(persist, **kw):
+        monkeypatch.setenv("TOPOPT_CG_PERSIST", "1" if persist else "0")
+        return t.FEASolver(t.CUDAMatrixFreeSolver, prob, penalty=t.PowerPenaltyFun(3.0), cg_variant=0, **kw)
+
+    for maxiter in (1, 5, 20, 61):
+        a, b = mk(False, cg_max_iter=maxiter, abstol=0.0, reltol=0.0), mk(True, cg_max_iter=maxiter, abstol=0.0, reltol=0.0)
+        a.vars = rho
+        b.vars = rho
+        ua, ub = a().copy(), b().copy()
+        assert a.last_result.iters == b.last_result.iters == maxiter
+        # rounding differences grow exponentially with the iteration count on these small high-contrast grids (both GPU
+        # paths leave the oracle together: 1e-16 / 3e-14 / 1e-10 / 1e-4 after 5 / 20 / 40 / 61 iterations on the 40x12 grid,
+        # tools/r02_probe_persist.py), so the long run only checks the batch boundary loosely
+        tol = 1e-12 if maxiter <= 5 else (1e-9 if maxiter <= 20 else 5e-3)
+        assert rel(ub, ua) < tol, (maxiter, rel(ub, ua))
+        assert abs(a.last_result.residual - b.last_result.residual) <= 10 * tol * a.last_result.residual
+        assert b.stats().kernel_launches < a.stats().kernel_launches or maxiter == 1
+        uo, it, res = o.solve_matfree(oprob, E, abstol=0.0, reltol=0.0, maxiter=maxiter)
+        assert rel(ub, uo) < tol
+        a.close()
+        b.close()
+    a, b = mk(False, abstol=1e-10, reltol=0.0, cg_max_iter=20000), mk(True, abstol=1e-10, reltol=0.0, cg_max_iter=20000)
+    a.vars = rho
+    b.vars = rho
+    ua, ub = a().copy(), b().copy()
+    assert a.last_result.converged == 1 and b.last_result.converged == 1
+    assert abs(a.last_result.iters - b.last_result.iters) <= 2 and rel(ub, ua) < 1e-8
+    assert rel(ub, o.solve_direct(oprob, E)) < 1e-7
+    a.close()
+    b.close()
+
+
 def test_warm_start_and_refreshed_jacobi(lib):
     """Opt-in extensions over the reference (solvers_api.jl:187-203): warm start from the resident solution
     and a Jacobi preconditioner rebuilt from the current stiffness reach the same solution in fewer

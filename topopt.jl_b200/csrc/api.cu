@@ -109,6 +109,8 @@ struct topopt_handle {
   int kxu_ring_min = 12;  // fewest owned node planes per rank for which the ring kernel is selected
   int kxu_grid = 0;       // ring kernel: explicit CTA count (0 = 148 x waves)
   int cg_fused_grid = 0;  // one-kernel iteration: explicit CTA count (0 = aligned_grid())
+  int cg_persist = 1;  // small single-GPU grids: whole batches of CG iterations in one cooperative kernel (k_cg_persistent)
+  unsigned int* d_barrier = nullptr;
   bool cg_fused_single_only = false;  // TOPOPT_CG_FUSED_MGPU=0: ranks of a multi-GPU run keep the two-kernel iteration
   int cg_fused = 1;       // single GPU, single-pass recurrence: one kernel per CG iteration (kxu_hex8_cgfused.cuh); 0 = off, else thread rows
   int cg_variant_env = -1;  // TOPOPT_CG_VARIANT overrides topopt_cg_opts.variant (diagnostics)
@@ -750,6 +752,47 @@ int launch_cg_apply(topopt_handle* h, bool peer_halo, int fin) {
   return launch_apply<true>(h, h->d_p, h->d_Ap, fin);
 }
 
+// ---- persistent CG for small grids (kernels.cuh: k_cg_persistent) ----
+template <int DIM, int NC>
+int launch_cg_persistent_t(topopt_handle* h, int niter) {
+  static std::atomic<int> blocks_per_sm{0};
+  int nb = blocks_per_sm.load();
+  if (nb == 0) {
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_cg_persistent<DIM, NC>, kBlock, 0));
+    blocks_per_sm.store(nb);
+  }
+  if (nb < 1) return TOPOPT_ERR_CUDA;
+  int sms = 0;
+  CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+  const long long nnodes = (long long)h->g.S * h->g.nown;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((long long)nb * sms, (nnodes + kBlock - 1) / kBlock));
+  if (2 * grid > kMaxPartialBlocks) return TOPOPT_ERR_CUDA;
+  if (!h->d_barrier) CUDA_TRY(h, cudaMalloc((void**)&h->d_barrier, sizeof(unsigned int)));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_barrier, 0, sizeof(unsigned int), h->stream));
+  Geo g = h->g;
+  double *x = h->d_u, *r = h->d_r, *p = h->d_p, *Ap = h->d_Ap, *partials = h->d_partials;
+  const double* E = h->d_E;
+  const unsigned char* fixed = h->d_fixed;
+  double fd = h->fixed_diag;
+  CGState* st = h->d_st;
+  unsigned int* bar = h->d_barrier;
+  void* args[] = {&g, &x, &r, &p, &Ap, &E, &fixed, &fd, &partials, &st, &bar, &niter};
+  const cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_cg_persistent<DIM, NC>, dim3(grid), dim3(kBlock), args, 0, h->stream);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return TOPOPT_ERR_CUDA;  // the caller falls back to one launch per kernel
+  }
+  h->stats.kernel_launches += 1;
+  return TOPOPT_OK;
+}
+
+int launch_cg_persistent(topopt_handle* h, int niter) {
+  if (h->dim == 2 && h->nc == 2) return launch_cg_persistent_t<2, 2>(h, niter);
+  if (h->dim == 2) return launch_cg_persistent_t<2, 1>(h, niter);
+  if (h->nc == 3) return launch_cg_persistent_t<3, 3>(h, niter);
+  return launch_cg_persistent_t<3, 1>(h, niter);
+}
+
 #include "mg_solve.inl"
 
 // IterativeSolvers cg!: see cg_finalize() for the scalar recurrences.
@@ -780,6 +823,11 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
   const bool single = want_variant == TOPOPT_CG_SINGLE_PASS && !pre && !energy && hex8 && use_ring(h) && (h->world == 1 || peer);
   // ... and on one GPU the whole iteration is one kernel (vector updates applied while the planes are staged)
   const bool fused = single && h->cg_fused != 0 && (h->world == 1 || (peer_halo && h->peer_fused_ready && !h->cg_fused_single_only));
+  // small grids, the reference's recurrence: batches of iterations in one cooperative kernel (launch latency, not bytes,
+  // is what an iteration costs there).  2-D grids and 3-D grids of at most ~200 k nodes; the large hex8 grids have
+  // the ring-staged / one-kernel paths above.
+  bool persist = h->cg_persist != 0 && h->world == 1 && !assembled && !pre && !energy && !single &&
+                 (h->dim == 2 || (long long)h->g.S * h->g.nown <= 200000);
   CGState& s = *h->h_st;
   std::memset(&s, 0, sizeof(CGState));
   s.abstol = ignore_convergence ? -1.0 : o->abstol;
@@ -899,6 +947,15 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
     };
     // Replay a captured graph of n iterations when nothing in the batch depends on host state:
     // single GPU or the peer-memory path (no NCCL calls inside), no fused pointer swap, no tracing.
+    if (persist && !trace) {
+      const int rc = launch_cg_persistent(h, n);
+      if (rc == TOPOPT_OK) {
+        TRY(check_launch(h, "k_cg_persistent"));
+        issued += n;
+        continue;
+      }
+      persist = false;  // cooperative launch not available here: one launch per kernel from now on
+    }
     const bool graphable = h->use_graphs && !trace && !fusep && (h->world == 1 || (peer && (peer_halo || assembled))) && issued > 0;
     if (graphable) {
       // every pointer and flag baked into the captured launches is part of the key
@@ -1351,6 +1408,7 @@ int topopt_create(const topopt_desc* d, topopt_handle** out) {
     if (const char* e = getenv("TOPOPT_CG_FUSED_TMA")) h->cg_fused_tma = atoi(e);
   }
   if (const char* e = getenv("TOPOPT_CG_VARIANT")) h->cg_variant_env = atoi(e);
+  if (const char* e = getenv("TOPOPT_CG_PERSIST")) h->cg_persist = atoi(e);
 
   // slab partition along the last axis
   const int NLg = (int)(h->dim == 3 ? gd.nz : gd.ny);
@@ -1505,6 +1563,7 @@ int topopt_destroy(topopt_handle* h) {
   mg_free(h->mg);
   h->mg = nullptr;
   if (h->d_tmaps) cudaFree(h->d_tmaps);
+  if (h->d_barrier) cudaFree(h->d_barrier);
   ipc_close_all(h);
   if (h->d_peerblock) cudaFree(h->d_peerblock);
   if (h->d_peercomm) cudaFree(h->d_peercomm);

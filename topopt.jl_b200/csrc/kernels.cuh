@@ -427,107 +427,121 @@ __host__ __device__ constexpr int corner_local(int ox, int oy, int op) {
   return DIM == 3 ? (((ox ^ oy) | (oy << 1)) + 4 * op) : ((ox ^ op) | (op << 1));
 }
 
-// y = K(E) x, node-centric gather (matrix_free_operator.jl:66-105): for each of the <= 2^DIM
-// adjacent elements (ascending cell id) accumulate row(Ke_bc) . x_e, scale by E_e, then add the
-// element contributions in ascending cell order.  Prescribed rows return fixed_diag * x.
-// DOT: also reduce sum_owned x.y into partials and run the CG scalar step `fin`.
+// One node of y = K(E) x, node-centric gather (matrix_free_operator.jl:66-105): for each of the <= 2^DIM adjacent
+// elements (ascending cell id) accumulate row(Ke_bc) . x_e, scale by E_e, then add the element contributions in
+// ascending cell order.  Prescribed rows return fixed_diag * x.  t = owned node index; returns the local node index.
+// x carries no __restrict__ here: k_cg_persistent writes the vector it passes between its phases, so its loads must stay
+// on the coherent path (k_apply's own parameter is const __restrict__, which still gives it the read-only path).
+template <int DIM, int NC>
+__device__ __forceinline__ long long apply_node(const Geo& g, const double* x, const double* __restrict__ E,
+                                                const unsigned char* __restrict__ fixed, double fixed_diag, long long t,
+                                                double (&yo)[NC], double (&xo)[NC]) {
+  constexpr int NQ = 1 << DIM;
+  constexpr int KS = NQ * NC;
+  constexpr int NYR = DIM == 3 ? 3 : 1;
+  constexpr int NEY = DIM == 3 ? 2 : 1;
+  const int inpl = (int)(t % g.S);
+  const int lp = (int)(t / g.S) + 1;
+  const int i = inpl % g.NX;
+  const int j = DIM == 3 ? inpl / g.NX : 0;
+  const int gk = lp + g.p0;  // global plane
+  double Eq[NQ];
+  double acc[NQ][NC];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int ex = q & 1, ey = DIM == 3 ? (q >> 1) & 1 : 0, ep = DIM == 3 ? (q >> 2) & 1 : (q >> 1) & 1;
+    const int ei = i - 1 + ex, ej = j - 1 + ey, el = lp - 1 + ep, egl = gk - 1 + ep;
+    bool ok = ei >= 0 && ei < g.nx && egl >= 0 && egl < g.NLg;
+    if (DIM == 3) ok = ok && ej >= 0 && ej < g.ny;
+    Eq[q] = ok ? E[(long long)el * g.SE + (DIM == 3 ? ej * g.nx : 0) + ei] : 0.0;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[q][c] = 0.0;
+  }
+  unsigned char fo = 0;
+#pragma unroll
+  for (int dp = 0; dp < 3; ++dp) {
+#pragma unroll
+    for (int dy = 0; dy < NYR; ++dy) {
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int ii = i - 1 + dx, jj = DIM == 3 ? j - 1 + dy : 0, pp = lp - 1 + dp, gp = gk - 1 + dp;
+        bool ok = ii >= 0 && ii < g.NX && gp >= 0 && gp < g.NPg;
+        if (DIM == 3) ok = ok && jj >= 0 && jj < g.NY;
+        double xb[NC];
+        unsigned char fb = 0;
+        if (ok) {
+          const long long ln = (long long)pp * g.S + (long long)jj * g.NX + ii;
+          fb = fixed[ln];
+#pragma unroll
+          for (int c = 0; c < NC; ++c) xb[c] = x[ln * NC + c];
+        } else {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) xb[c] = 0.0;
+        }
+        if (dp == 1 && dx == 1 && (DIM == 2 || dy == 1)) {
+          fo = fb;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) xo[c] = xb[c];
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+          if (fb & (1 << c)) xb[c] = 0.0;  // bcmatrix: constrained columns are zero
+#pragma unroll
+        for (int ep = 0; ep < 2; ++ep) {
+          const int op = dp - ep;
+          if (op < 0 || op > 1) continue;
+#pragma unroll
+          for (int ey = 0; ey < NEY; ++ey) {
+            const int oy = DIM == 3 ? dy - ey : 0;
+            if (oy < 0 || oy > 1) continue;
+#pragma unroll
+            for (int ex = 0; ex < 2; ++ex) {
+              const int ox = dx - ex;
+              if (ox < 0 || ox > 1) continue;
+              const int q = DIM == 3 ? ex + 2 * ey + 4 * ep : ex + 2 * ep;
+              const int aloc = corner_local<DIM>(1 - ex, 1 - ey, 1 - ep);
+              const int bloc = corner_local<DIM>(ox, oy, op);
+#pragma unroll
+              for (int c = 0; c < NC; ++c)
+#pragma unroll
+                for (int c2 = 0; c2 < NC; ++c2)
+                  acc[q][c] = fma(cKe[(NC * aloc + c) + KS * (NC * bloc + c2)], xb[c2], acc[q][c]);
+            }
+          }
+        }
+      }
+    }
+  }
+  const long long ln = (long long)lp * g.S + inpl;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    double v = 0.0;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) v += Eq[q] * acc[q][c];
+    if (fo & (1 << c)) v = fixed_diag * xo[c];
+    yo[c] = v;
+  }
+  return ln;
+}
+
+// y = K(E) x on the owned nodes.  DOT: also reduce sum_owned x.y into partials and run the CG scalar step `fin`.
 template <int DIM, int NC, bool DOT>
 __global__ void __launch_bounds__(kBlock) k_apply(Geo g, const double* __restrict__ x, double* __restrict__ y,
                                                   const double* __restrict__ E,
                                                   const unsigned char* __restrict__ fixed, double fixed_diag,
                                                   double* partials, CGState* st, int fin) {
-  constexpr int NQ = 1 << DIM;
-  constexpr int KS = NQ * NC;
-  constexpr int NYR = DIM == 3 ? 3 : 1;
-  constexpr int NEY = DIM == 3 ? 2 : 1;
   __shared__ double sm[32];
   if (DOT && st->done) return;
   const long long nown = (long long)g.S * g.nown;
   double dot = 0.0;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nown;
        t += (long long)gridDim.x * blockDim.x) {
-    const int inpl = (int)(t % g.S);
-    const int lp = (int)(t / g.S) + 1;
-    const int i = inpl % g.NX;
-    const int j = DIM == 3 ? inpl / g.NX : 0;
-    const int gk = lp + g.p0;  // global plane
-    double Eq[NQ];
-    double acc[NQ][NC];
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const int ex = q & 1, ey = DIM == 3 ? (q >> 1) & 1 : 0, ep = DIM == 3 ? (q >> 2) & 1 : (q >> 1) & 1;
-      const int ei = i - 1 + ex, ej = j - 1 + ey, el = lp - 1 + ep, egl = gk - 1 + ep;
-      bool ok = ei >= 0 && ei < g.nx && egl >= 0 && egl < g.NLg;
-      if (DIM == 3) ok = ok && ej >= 0 && ej < g.ny;
-      Eq[q] = ok ? E[(long long)el * g.SE + (DIM == 3 ? ej * g.nx : 0) + ei] : 0.0;
-#pragma unroll
-      for (int c = 0; c < NC; ++c) acc[q][c] = 0.0;
-    }
-    double xo[NC];
-    unsigned char fo = 0;
-#pragma unroll
-    for (int dp = 0; dp < 3; ++dp) {
-#pragma unroll
-      for (int dy = 0; dy < NYR; ++dy) {
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          const int ii = i - 1 + dx, jj = DIM == 3 ? j - 1 + dy : 0, pp = lp - 1 + dp, gp = gk - 1 + dp;
-          bool ok = ii >= 0 && ii < g.NX && gp >= 0 && gp < g.NPg;
-          if (DIM == 3) ok = ok && jj >= 0 && jj < g.NY;
-          double xb[NC];
-          unsigned char fb = 0;
-          if (ok) {
-            const long long ln = (long long)pp * g.S + (long long)jj * g.NX + ii;
-            fb = fixed[ln];
-#pragma unroll
-            for (int c = 0; c < NC; ++c) xb[c] = x[ln * NC + c];
-          } else {
-#pragma unroll
-            for (int c = 0; c < NC; ++c) xb[c] = 0.0;
-          }
-          if (dp == 1 && dx == 1 && (DIM == 2 || dy == 1)) {
-            fo = fb;
-#pragma unroll
-            for (int c = 0; c < NC; ++c) xo[c] = xb[c];
-          }
-#pragma unroll
-          for (int c = 0; c < NC; ++c)
-            if (fb & (1 << c)) xb[c] = 0.0;  // bcmatrix: constrained columns are zero
-#pragma unroll
-          for (int ep = 0; ep < 2; ++ep) {
-            const int op = dp - ep;
-            if (op < 0 || op > 1) continue;
-#pragma unroll
-            for (int ey = 0; ey < NEY; ++ey) {
-              const int oy = DIM == 3 ? dy - ey : 0;
-              if (oy < 0 || oy > 1) continue;
-#pragma unroll
-              for (int ex = 0; ex < 2; ++ex) {
-                const int ox = dx - ex;
-                if (ox < 0 || ox > 1) continue;
-                const int q = DIM == 3 ? ex + 2 * ey + 4 * ep : ex + 2 * ep;
-                const int aloc = corner_local<DIM>(1 - ex, 1 - ey, 1 - ep);
-                const int bloc = corner_local<DIM>(ox, oy, op);
-#pragma unroll
-                for (int c = 0; c < NC; ++c)
-#pragma unroll
-                  for (int c2 = 0; c2 < NC; ++c2)
-                    acc[q][c] = fma(cKe[(NC * aloc + c) + KS * (NC * bloc + c2)], xb[c2], acc[q][c]);
-              }
-            }
-          }
-        }
-      }
-    }
-    const long long ln = (long long)lp * g.S + inpl;
+    double v[NC], xo[NC];
+    const long long ln = apply_node<DIM, NC>(g, x, E, fixed, fixed_diag, t, v, xo);
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      double v = 0.0;
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) v += Eq[q] * acc[q][c];
-      if (fo & (1 << c)) v = fixed_diag * xo[c];
-      y[ln * NC + c] = v;
-      if (DOT) dot = fma(xo[c], v, dot);
+      y[ln * NC + c] = v[c];
+      if (DOT) dot = fma(xo[c], v[c], dot);
     }
   }
   if (DOT) {
@@ -756,6 +770,94 @@ __global__ void __launch_bounds__(kBlock) k_update_xrp(long long off, long long 
     range(0, n);
     block_partials_finish<1>(v, partials, st, FIN_RR2, sm, halo_n > 0);
   }
+}
+
+// ---- persistent CG for small grids (launch-latency bound: 3 launches + 2 device-wide reductions per iteration cost
+// ~27 us at configs 1 / 3 for < 2 MB of traffic).  One cooperative launch runs `niter` iterations of IterativeSolvers'
+// recurrence (identity preconditioner, default criteria) with three device-wide barriers per iteration; every block sums
+// the per-block partials in the same fixed order and runs cg_finalize on its own copy of the scalar state, so no block
+// waits for another one's scalars.  All blocks must be co-resident (cudaLaunchCooperativeKernel).
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int nblocks, unsigned int& epoch) {
+  __syncthreads();
+  epoch += 1;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const unsigned int target = epoch * nblocks;
+    while (*(volatile unsigned int*)counter < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int DIM, int NC>
+__global__ void __launch_bounds__(kBlock) k_cg_persistent(Geo g, double* __restrict__ x, double* __restrict__ r, double* __restrict__ p,
+                                                          double* __restrict__ Ap, const double* __restrict__ E,
+                                                          const unsigned char* __restrict__ fixed, double fixed_diag, double* partials,
+                                                          CGState* st, unsigned int* barrier_counter, int niter) {
+  __shared__ double sm[32];
+  __shared__ CGState ls;  // this block's copy of the scalar state (identical on every block)
+  __shared__ double total;
+  const long long off = (long long)g.S * NC, n = (long long)g.S * g.nown * NC, nnodes = (long long)g.S * g.nown;
+  const long long tid0 = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  if (threadIdx.x == 0) ls = *st;
+  __syncthreads();
+  unsigned int epoch = 0;
+  double* part[2] = {partials, partials + gridDim.x};
+  // sum of the per-block partials in a fixed order (every block computes the same bits)
+  auto reduce_all = [&](const double* pp) -> double {
+    double a = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) a += __ldcg(&pp[b]);
+    a = block_sum(a, sm);
+    if (threadIdx.x == 0) total = a;
+    __syncthreads();
+    return total;
+  };
+  for (int it = 0; it < niter; ++it) {
+    if (ls.done) break;
+    const double beta = ls.beta;
+    for (long long t = tid0; t < n; t += stride) p[off + t] = fma(beta, p[off + t], r[off + t]);  // k_update_p
+    grid_barrier(barrier_counter, gridDim.x, epoch);
+    double dot = 0.0;
+    for (long long t = tid0; t < nnodes; t += stride) {  // k_apply<DIM, NC, true>
+      double v[NC], xo[NC];
+      const long long ln = apply_node<DIM, NC>(g, p, E, fixed, fixed_diag, t, v, xo);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        Ap[ln * NC + c] = v[c];
+        dot = fma(xo[c], v[c], dot);
+      }
+    }
+    dot = block_sum(dot, sm);
+    if (threadIdx.x == 0) part[0][blockIdx.x] = dot;
+    grid_barrier(barrier_counter, gridDim.x, epoch);
+    const double pAp = reduce_all(part[0]);
+    if (threadIdx.x == 0) {
+      ls.gsums[0] = ls.sums[0] = pAp;
+      cg_finalize(&ls, FIN_PAP);
+    }
+    __syncthreads();
+    const double alpha = ls.alpha;
+    double rr = 0.0;
+    for (long long t = tid0; t < n; t += stride) {  // k_update_xr<false>
+      const long long k = off + t;
+      x[k] = fma(alpha, p[k], x[k]);
+      const double rv = fma(-alpha, Ap[k], r[k]);
+      r[k] = rv;
+      rr = fma(rv, rv, rr);
+    }
+    rr = block_sum(rr, sm);
+    if (threadIdx.x == 0) part[1][blockIdx.x] = rr;
+    grid_barrier(barrier_counter, gridDim.x, epoch);
+    const double rrs = reduce_all(part[1]);
+    if (threadIdx.x == 0) {
+      ls.gsums[0] = ls.sums[0] = rrs;
+      cg_finalize(&ls, FIN_RR);
+    }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *st = ls;
 }
 
 // plain dot over owned dofs -> st->sums[0]
