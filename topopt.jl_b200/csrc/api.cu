@@ -546,10 +546,10 @@ int launch_cg_fused_t(topopt_handle* h, int fin) {
   v.x = h->d_u;
   for (int k = 0; k < 3; ++k)
     for (int par = 0; par < 2; ++par) {
-      const double* lo = PEER ? h->peer_lo[2 * k + par] : nullptr;
-      const double* hi = PEER ? h->peer_hi[2 * k + par] : nullptr;
-      v.lo[k][par] = lo ? lo + (size_t)h->plane_dofs * h->nown_lower : nullptr;  // the lower neighbour's top owned plane
-      v.hi[k][par] = hi ? hi + (size_t)h->plane_dofs : nullptr;                  // the upper neighbour's first owned plane
+      double* lo = PEER ? const_cast<double*>(h->peer_lo[2 * k + par]) : nullptr;
+      double* hi = PEER ? const_cast<double*>(h->peer_hi[2 * k + par]) : nullptr;
+      v.wlo[k][par] = lo ? lo + (size_t)h->plane_dofs * (h->nown_lower + 1) : nullptr;  // the lower neighbour's top ghost plane
+      v.whi[k][par] = hi;                                                               // the upper neighbour's bottom ghost plane
     }
   if (h->modal_cube && h->kxu_cube) {
     static std::atomic<unsigned long long> attr_mask{0};
@@ -664,6 +664,8 @@ int launch_cg_tma_t(topopt_handle* h, int fin) {
 
 int launch_cg_fused(topopt_handle* h, bool peer, int fin) {
   const int rows = fused_rows(h);
+  const bool force_peer_code = getenv("TOPOPT_CG_FUSED_FORCE_PEER_CODE") != nullptr;  // diagnostic: PEER instantiation on one GPU
+  if (force_peer_code && !h->cg_fused_tma) peer = true;
   if (h->cg_fused_tma) {
     if (peer) return rows == 8 ? launch_cg_tma_t<8, true>(h, fin) : launch_cg_tma_t<10, true>(h, fin);
     return rows == 8 ? launch_cg_tma_t<8, false>(h, fin) : launch_cg_tma_t<10, false>(h, fin);
@@ -864,7 +866,15 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
     h->stats.kernel_launches += 1;
   }
   // Ap_0 = K p_0, alpha_0, beta_0: every later iteration is one launch (multi-GPU: and tell the neighbours Ap_0 is final)
-  if (fused) TRY(launch_cg_apply<2>(h, peer_halo, FIN_PAP2 | (peer_halo ? 0x100 : 0)));
+  if (fused) {
+    TRY(launch_cg_apply<2>(h, peer_halo, FIN_PAP2 | (peer_halo ? 0x100 : 0)));
+    if (peer_halo && !h->cg_fused_tma) {
+      // the one-kernel iteration stages its ghost planes from local memory (the neighbours push them from then on)
+      TRY(exchange_halo(h, h->d_p));
+      TRY(exchange_halo(h, h->d_r));
+      TRY(exchange_halo(h, h->d_Ap));
+    }
+  }
   int batch = o->check_every > 0 ? o->check_every : (h->ndof > 2000000 ? 25 : 50);
   int issued = 0;
   const int maxiter = s.maxiter;
@@ -2163,6 +2173,14 @@ int topopt_oc_update(topopt_handle* h, const double* x, const double* dc, const 
 }
 
 // ---- measurement ------------------------------------------------------------------------------
+#ifdef TOPOPT_TIMELINE
+int topopt_debug_timeline(topopt_handle* h, unsigned long long* out) {
+  TRY(use_device(h));
+  CUDA_TRY(h, cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned long long) * 2 * 512 * 4));
+  return TOPOPT_OK;
+}
+#endif
+
 int topopt_time_kernel(topopt_handle* h, topopt_filter* f, int32_t which, int32_t reps, double* ms_out) {
   if (!h || !ms_out || reps < 1) return fail(h, TOPOPT_ERR_INVALID, "topopt_time_kernel: bad argument");
   TRY(use_device(h));

@@ -192,7 +192,8 @@ __device__ __forceinline__ void block_partials_finish(const double (&v)[NS], dou
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int k = 0; k < NS; ++k) partials[blockIdx.x * NS + k] = r[k];
-    __threadfence();
+    // signal_halo: this kernel may have written into the neighbours' memory (pushed boundary planes): system scope
+    if (signal_halo) __threadfence_system(); else __threadfence();
     const unsigned int t = atomicInc(&st->counter, gridDim.x - 1);
     is_last = (t == gridDim.x - 1);
   }
@@ -200,7 +201,7 @@ __device__ __forceinline__ void block_partials_finish(const double (&v)[NS], dou
   if (!is_last) return;
   __threadfence();
   // every block's stores are visible now: the vector this kernel wrote may be read by the neighbours
-  if (signal_halo && threadIdx.x == 0) signal_halo_flags(st);
+  if (signal_halo && threadIdx.x == 0 && st->peer != nullptr) signal_halo_flags(st);
   double a[NS];
 #pragma unroll
   for (int k = 0; k < NS; ++k) a[k] = 0.0;

@@ -39,22 +39,41 @@ __host__ __device__ constexpr size_t hex8_fused_smem(int tyt, int nst) {
          sizeof(double) * 2 * 3 * 32 * tyt + sizeof(double) * 2 * 6 * (tyt + 1) * 32;
 }
 
+#ifdef TOPOPT_TIMELINE  // diagnostic build: %globaltimer stamps of two consecutive iterations (tools/r02_timeline.py)
+__device__ unsigned long long g_tl[2][512][4];
+__device__ __forceinline__ unsigned long long tl_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TL_STAMP(ev)                                                              \
+  do {                                                                            \
+    if (tl_slot >= 0 && tl_slot < 2 && blockIdx.x < 512) g_tl[tl_slot][blockIdx.x][ev] = tl_now(); \
+  } while (0)
+#else
+#define TL_STAMP(ev) \
+  do {               \
+  } while (0)
+#endif
+
 struct CGFusedVecs {
   double* p[2];
   double* r[2];
   double* ap[2];
   double* x;
-  // multi-GPU (PEER): the slab neighbours' boundary planes of the same six buffers, [p, r, Ap][parity], mapped over
-  // cudaIpc; lo = the lower neighbour's top owned plane (this rank's ghost plane 0), hi = the upper neighbour's first
-  // owned plane (ghost plane nown + 1).  NULL at the ends of the slab stack.
-  const double* lo[3][2];
-  const double* hi[3][2];
+  // multi-GPU (PEER): the slab neighbours' GHOST planes of the same six buffers, [p, r, Ap][parity], mapped over cudaIpc;
+  // wlo = the lower neighbour's top ghost plane (receives this rank's plane 1), whi = the upper neighbour's bottom ghost
+  // plane (receives this rank's plane nown).  NULL at the ends of the slab stack.
+  double* wlo[3][2];
+  double* whi[3][2];
 };
 
-// PEER: the ghost planes are bulk-copied straight from the neighbours' memory once their previous kernel (iteration
-// k - 1: all of p, r, Ap final, scalars all-reduced) has signalled; this kernel signals in turn from its last CTA.  The
-// ping-pong parity keeps a neighbour that is one kernel ahead from overwriting what is still being read: it cannot
-// start iteration k + 1 before this rank has posted its sums of iteration k, which it does after its last read.
+// PEER: a rank PUSHES the boundary planes of p_k, r_k, Ap_k it forms into its neighbours' ghost planes (posted NVLink
+// stores next to the local ones) and signals from its last CTA; the next kernel stages its ghost planes from LOCAL memory
+// once the neighbours' signal of the previous kernel is in.  (Pulling them with bulk copies from the neighbours' memory
+// cost ~0.4 us per 800-byte request: 25 us on the critical CTAs of a 2-rank run, profiles/r02_timeline_n2_remote_reads.log.)
+// The ping-pong parity keeps a neighbour that is one kernel ahead from overwriting ghost planes that are still being read:
+// it cannot start iteration k + 1 before this rank has posted its sums of iteration k, which it does after its last read.
 template <int TYT, int NST, bool CUBE, bool PEER>
 __global__ void __launch_bounds__(32 * (TYT + kFusedProducers), 1)
     k_cg_fused_hex8(Geo g, CGFusedVecs vec, const double* __restrict__ E, const unsigned char* __restrict__ fixed, double fixed_diag,
@@ -78,6 +97,9 @@ __global__ void __launch_bounds__(32 * (TYT + kFusedProducers), 1)
   __shared__ double sm[32];
   if (st->done) return;
   const int parity = st->iters & 1;
+#ifdef TOPOPT_TIMELINE
+  const int tl_slot = st->iters - 300;
+#endif
   const double alpha = st->alpha, beta = st->beta;
   const double* __restrict__ pin = vec.p[parity];
   const double* __restrict__ rin = vec.r[parity];
@@ -109,6 +131,7 @@ __global__ void __launch_bounds__(32 * (TYT + kFusedProducers), 1)
   const long long units = (long long)tilesX * tilesY * g.nown;
   long long u0 = units * blockIdx.x / gridDim.x;
   const long long u1 = units * (blockIdx.x + 1) / gridDim.x;
+  if (tid == 0) TL_STAMP(0);
 
   if (producer) {
     // =========================== producer warp ===========================
@@ -121,8 +144,6 @@ __global__ void __launch_bounds__(32 * (TYT + kFusedProducers), 1)
       long long su0;
       long long idx;
       const double* src;
-      const double* glo;  // PEER: source of ghost plane 0 / nown + 1 (NULL: local)
-      const double* ghi;
       int P, last;
       int dst, dst_stride, w, k, clip;
       unsigned fcount;
@@ -146,8 +167,6 @@ __global__ void __launch_bounds__(32 * (TYT + kFusedProducers), 1)
         J.k = 2;
       }
       J.src = v == 0 ? pin : (v == 1 ? rin : apin);
-      J.glo = PEER ? vec.lo[v][parity] : nullptr;
-      J.ghi = PEER ? vec.hi[v][parity] : nullptr;
       J.stg = v != 0;
       // destination of stage 0 and the distance between stages (the staging area reuses slot `stage & 1`)
       if (v == 0) {
@@ -169,8 +188,25 @@ __global__ void __launch_bounds__(32 * (TYT + kFusedProducers), 1)
       J.ok = false;
       J.clip = 0;
     }
+    if (PEER && st->peer != nullptr) {
+      // The ghost planes of this kernel's inputs were pushed into local memory by the neighbours' previous kernel: wait for
+      // their signal ONCE, before the first copy.  (It was raised before they posted the sums this rank's previous kernel
+      // waited for, so this does not spin; PEER code inside the copy loop cost 30 us per launch.)
+      PeerComm* pc = st->peer;
+      const volatile unsigned long long* f = pc->block[pc->rank]->halo_flag;
+      const bool need_lo = vec.wlo[0][0] != nullptr, need_hi = vec.whi[0][0] != nullptr;
+      long long spins = 0;
+      while ((need_lo && f[0] < pc->halo_seq) || (need_hi && f[1] < pc->halo_seq)) {
+        if (++spins > kSpinLimit / 8) {
+          pc->timeout = 1;  // a dead peer must not hang the GPU: proceed, the solve reports the error
+          break;
+        }
+      }
+      // No fence: the neighbour ordered its plane stores before its flag store (system-scope fence on its side), both land
+      // in THIS GPU's L2, and the bulk copies below are issued after the loop has seen the flag and read through L2.  (A
+      // system-scope fence here cost every CTA ~4 us before its first copy.)
+    }
     bool alldone;
-    long long halo_spins = 0;
     do {
       bool progressed = false;
       alldone = true;
@@ -200,28 +236,9 @@ __global__ void __launch_bounds__(32 * (TYT + kFusedProducers), 1)
         }
         alldone = false;
         const int sidx = (int)(J.fcount % NST);
-        bool ready = J.stg ? (J.fcount < 2 || mbar_test_wait(&sempty[J.w][J.fcount & 1u], ((J.fcount >> 1) + 1u) & 1u))
+        const bool ready = J.stg ? (J.fcount < 2 || mbar_test_wait(&sempty[J.w][J.fcount & 1u], ((J.fcount >> 1) + 1u) & 1u))
                            : (J.fcount < NST || mbar_test_wait(&empty[J.w][sidx], ((J.fcount / NST) + 1u) & 1u));
         const char* plane = reinterpret_cast<const char*>(J.src + (long long)J.P * g.S * 3);
-        if (PEER) {
-          const bool glo = J.glo != nullptr && J.P == 0, ghi = J.ghi != nullptr && J.P == g.nown + 1;
-          if (glo || ghi) {
-            PeerComm* pc = st->peer;
-            const volatile unsigned long long* f = pc->block[pc->rank]->halo_flag;
-            if (f[glo ? 0 : 1] < pc->halo_seq) {
-              if (++halo_spins > kSpinLimit / 8) {
-                pc->timeout = 1;  // a dead peer must not hang the GPU: proceed, the solve reports the error
-              } else {
-                ready = false;
-              }
-            }
-            plane = reinterpret_cast<const char*>(glo ? J.glo : J.ghi);
-            if (ready) {
-              __threadfence_system();
-              asm volatile("fence.proxy.async;" ::: "memory");
-            }
-          }
-        }
         if (ready) {
           uint64_t* bar = &full[J.w][sidx];
           if (J.ok) {
@@ -288,13 +305,9 @@ __global__ void __launch_bounds__(32 * (TYT + kFusedProducers), 1)
       const unsigned leadN0 = (unsigned)(((long long)r0 * g.NX + c_lo) & 1) << 3;
       const unsigned leadNB = leadN0 ^ ((unsigned)(g.NX & 1) << 3);
       auto plane_lead = [&](int P) -> unsigned {
-        const double* pp = pin + (long long)P * g.S * 3;
-        if (PEER) {  // p, r and Ap of a neighbour share their 16-byte alignment (separate cudaMalloc allocations)
-          if (vec.lo[0][parity] != nullptr && P == 0) pp = vec.lo[0][parity];
-          if (vec.hi[0][parity] != nullptr && P == g.nown + 1) pp = vec.hi[0][parity];
-        }
-        return (unsigned)(reinterpret_cast<uintptr_t>(pp) & 8);
+        return (unsigned)(reinterpret_cast<uintptr_t>(pin + (long long)P * g.S * 3) & 8);
       };
+
       // ---- combine bookkeeping: lane tx handles the flat values v = tx + 32 j (v = 3 node + comp) of a 33-node row
       unsigned vmask = 0, omask = 0;  // bit j: value in the domain / value of a node this tile owns (columns 1..31)
 #pragma unroll
@@ -380,6 +393,7 @@ __global__ void __launch_bounds__(32 * (TYT + kFusedProducers), 1)
               pout[gi] = pn;
               xsol[gi] = fma(alpha, po, xs[k][j < 3 ? j : 0][tx]);
               dots[2] = fma(rn, rn, dots[2]);
+
             }
           }
         }
@@ -419,6 +433,9 @@ __global__ void __launch_bounds__(32 * (TYT + kFusedProducers), 1)
 
       int s_tail = sf, s_old = sf, s_new = next_stage(sf);
       wait_stage(s_old, false);
+#ifdef TOPOPT_TIMELINE
+      if (ty == 0 && tx == 0 && it == 0) TL_STAMP(1);
+#endif
       combine(first, s_old);  // not an owned plane: no x
       issue_x(first + 1);
       bool hint_new = false;
@@ -590,7 +607,41 @@ __global__ void __launch_bounds__(32 * (TYT + kFusedProducers), 1)
       sf = s_new;
     }  // segments
   }
+  if (PEER) {
+    // Push pass: the boundary planes (1 and nown) of p_k, r_k, Ap_k that this CTA's segments own go to the neighbours'
+    // ghost planes -- re-read from this rank's memory (L2-hot, written by this CTA) and stored over NVLink by all threads.
+    // Kept out of the plane loop: pushes inside the combine / tail cost every step registers and predicates.
+    __syncthreads();
+    long long su = units * blockIdx.x / gridDim.x;
+    const long long ystep = (long long)g.S * 3;
+    while (su < u1) {
+      const int tile = (int)(su / g.nown);
+      const int zoff = (int)(su % g.nown);
+      const int zlen = (int)min((long long)(g.nown - zoff), u1 - su);
+      su += zlen;
+      const int bx = tile % tilesX, by = tile / tilesX;
+      const int rlo = by * OWNR, rhi = min(rlo + OWNR, g.NY), clo = bx * 31, chi = min(clo + 31, g.NX);
+      const int ncv = (chi - clo) * 3, nrows = rhi - rlo;
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        const int P = side == 0 ? 1 : g.nown;
+        const bool mine = side == 0 ? zoff == 0 : zoff + zlen == g.nown;
+        double* dp = side == 0 ? (parity ? vec.wlo[0][0] : vec.wlo[0][1]) : (parity ? vec.whi[0][0] : vec.whi[0][1]);
+        double* dr = side == 0 ? (parity ? vec.wlo[1][0] : vec.wlo[1][1]) : (parity ? vec.whi[1][0] : vec.whi[1][1]);
+        double* da = side == 0 ? (parity ? vec.wlo[2][0] : vec.wlo[2][1]) : (parity ? vec.whi[2][0] : vec.whi[2][1]);
+        if (!mine || dp == nullptr || ncv <= 0 || nrows <= 0) continue;
+        for (int idx = tid; idx < nrows * ncv; idx += (int)blockDim.x) {
+          const long long off = ((long long)(rlo + idx / ncv) * g.NX + clo) * 3 + idx % ncv;
+          dp[off] = __ldcg(pout + P * ystep + off);
+          dr[off] = __ldcg(rout + P * ystep + off);
+          da[off] = __ldcg(y + P * ystep + off);
+        }
+      }
+    }
+  }
+  if (tid == 0) TL_STAMP(2);
   block_partials_finish<3>(dots, partials, st, fin, sm, PEER);
+  if (tid == 0) TL_STAMP(3);
 }
 
 }  // namespace topopt
