@@ -666,10 +666,8 @@ int launch_cg_fused(topopt_handle* h, bool peer, int fin) {
   const int rows = fused_rows(h);
   const bool force_peer_code = getenv("TOPOPT_CG_FUSED_FORCE_PEER_CODE") != nullptr;  // diagnostic: PEER instantiation on one GPU
   if (force_peer_code && !h->cg_fused_tma) peer = true;
-  if (h->cg_fused_tma) {
-    if (peer) return rows == 8 ? launch_cg_tma_t<8, true>(h, fin) : launch_cg_tma_t<10, true>(h, fin);
-    return rows == 8 ? launch_cg_tma_t<8, false>(h, fin) : launch_cg_tma_t<10, false>(h, fin);
-  }
+  // the tensor-map variant is single-GPU (its multi-GPU instantiation pulls ghost planes and was never run across ranks)
+  if (h->cg_fused_tma && !peer) return rows == 8 ? launch_cg_tma_t<8, false>(h, fin) : launch_cg_tma_t<10, false>(h, fin);
   if (peer) return rows == 8 ? launch_cg_fused_t<8, true>(h, fin) : launch_cg_fused_t<10, true>(h, fin);
   return rows == 8 ? launch_cg_fused_t<8, false>(h, fin) : launch_cg_fused_t<10, false>(h, fin);
 }
@@ -868,7 +866,7 @@ int cg_solve(topopt_handle* h, const double* b, const topopt_cg_opts* o, topopt_
   // Ap_0 = K p_0, alpha_0, beta_0: every later iteration is one launch (multi-GPU: and tell the neighbours Ap_0 is final)
   if (fused) {
     TRY(launch_cg_apply<2>(h, peer_halo, FIN_PAP2 | (peer_halo ? 0x100 : 0)));
-    if (peer_halo && !h->cg_fused_tma) {
+    if (peer_halo) {
       // the one-kernel iteration stages its ghost planes from local memory (the neighbours push them from then on)
       TRY(exchange_halo(h, h->d_p));
       TRY(exchange_halo(h, h->d_r));
