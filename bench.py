@@ -361,8 +361,10 @@ def run_native(args, nels):
     kxu_which = 8 if (single and ring) else 0
     kxu_ms = solver.time_kernel(kxu_which, args.kernel_reps)
     cg_ms = solver.time_kernel(9 if single and ring else 1, max(args.kernel_reps, 200))
-    # single GPU + single-pass recurrence: the whole CG iteration is ONE kernel (kxu_hex8_cgfused.cuh); it is the dominant kernel
-    fused = single and ring and world == 1 and os.environ.get("TOPOPT_CG_FUSED", "1") != "0"
+    # single-pass recurrence on hex8 slabs: the whole CG iteration is ONE kernel (kxu_hex8_cgfused.cuh), on one GPU and -- over
+    # peer memory -- across ranks; it is the dominant kernel of the step
+    fused = (single and ring and os.environ.get("TOPOPT_CG_FUSED", "1") != "0"
+             and (world == 1 or os.environ.get("TOPOPT_CG_FUSED_MGPU", "1") != "0"))
     cg_ref_ms = solver.time_kernel(1, args.kernel_reps)
     kxu_prev_ms = solver.time_kernel(7, args.kernel_reps)
     sens_ms = solver.time_kernel(2, 5)
@@ -386,10 +388,11 @@ def run_native(args, nels):
         # read p, r, Ap, x and write p, r, Ap, x (64 B per dof) + E_e (8 B per element): DESIGN.md section 4
         roof_name = ("k_cg_fused_hex8 (one CG iteration per launch: x += a p, r -= a Ap, p = r + b p applied while the planes are staged, "
                      "matrix-free hex8 K.p, fused p.Ap / Ap.Ap / r.r and scalar step)")
-        roof_bytes = 64 * prob.ndof + 8 * prob.nel
+        roof_bytes = (64 * prob.ndof + 8 * prob.nel) / world  # one launch per rank over its slab
         roof_ms = cg_ms
         roof_traffic = ncu_traffic(world, "cg_fused_dram_bytes_per_launch") if nels == DEFAULT_NELS else None
-        roof_timed = "inside the CG loop on a dense right-hand side (topopt_time_kernel class 9: solve time / iterations, graph-replayed launches)"
+        roof_timed = ("inside the CG loop on a dense right-hand side (topopt_time_kernel class 9: solve time / iterations, graph-replayed launches"
+                      + ("; includes the in-kernel all-reduce wait for the slowest rank)" if world > 1 else ")"))
     else:
         roof_name, roof_bytes, roof_ms, roof_traffic = kxu_name, kxu_bytes_launch, kxu_ms, kxu_alone["traffic"]
         roof_timed = "dense direction vector (zero on prescribed dofs), fused dot products, the variant the CG loop launches"
