@@ -109,6 +109,7 @@ struct topopt_handle {
   int kxu_ring_min = 12;  // fewest owned node planes per rank for which the ring kernel is selected
   int kxu_grid = 0;       // ring kernel: explicit CTA count (0 = 148 x waves)
   int cg_fused_grid = 0;  // one-kernel iteration: explicit CTA count (0 = aligned_grid())
+  int cg_fused_pdl = 1;  // one-kernel iteration: programmatic dependent launch (prologue overlaps the previous kernel's tail)
   int cg_persist = 1;  // small single-GPU grids: whole batches of CG iterations in one cooperative kernel (k_cg_persistent)
   unsigned int* d_barrier = nullptr;
   bool cg_fused_single_only = false;  // TOPOPT_CG_FUSED_MGPU=0: ranks of a multi-GPU run keep the two-kernel iteration
@@ -551,17 +552,30 @@ int launch_cg_fused_t(topopt_handle* h, int fin) {
       v.wlo[k][par] = lo ? lo + (size_t)h->plane_dofs * (h->nown_lower + 1) : nullptr;  // the lower neighbour's top ghost plane
       v.whi[k][par] = hi;                                                               // the upper neighbour's bottom ghost plane
     }
+  // programmatic dependent launch: this kernel's CTAs may run their prologue while the previous iteration's kernel finishes
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(32 * (TYT + kFusedProducers));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = h->cg_fused_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const double* dE = h->d_E;
+  const unsigned char* dfix = h->d_fixed;
+  cudaError_t le;
   if (h->modal_cube && h->kxu_cube) {
     static std::atomic<unsigned long long> attr_mask{0};
     TRY(ensure_dyn_smem(h, k_cg_fused_hex8<TYT, NST, true, PEER>, smem, attr_mask));
-    k_cg_fused_hex8<TYT, NST, true, PEER><<<grid, 32 * (TYT + kFusedProducers), smem, h->stream>>>(g, v, h->d_E, h->d_fixed, h->fixed_diag, tilesX,
-                                                                                   tilesY, h->d_partials, h->d_st, fin);
+    le = cudaLaunchKernelEx(&cfg, k_cg_fused_hex8<TYT, NST, true, PEER>, g, v, dE, dfix, h->fixed_diag, tilesX, tilesY, h->d_partials, h->d_st, fin);
   } else {
     static std::atomic<unsigned long long> attr_mask{0};
     TRY(ensure_dyn_smem(h, k_cg_fused_hex8<TYT, NST, false, PEER>, smem, attr_mask));
-    k_cg_fused_hex8<TYT, NST, false, PEER><<<grid, 32 * (TYT + kFusedProducers), smem, h->stream>>>(g, v, h->d_E, h->d_fixed, h->fixed_diag, tilesX,
-                                                                                    tilesY, h->d_partials, h->d_st, fin);
+    le = cudaLaunchKernelEx(&cfg, k_cg_fused_hex8<TYT, NST, false, PEER>, g, v, dE, dfix, h->fixed_diag, tilesX, tilesY, h->d_partials, h->d_st, fin);
   }
+  if (le != cudaSuccess) return fail(h, TOPOPT_ERR_CUDA, std::string("k_cg_fused_hex8 launch: ") + cudaGetErrorString(le));
   h->stats.kernel_launches += 1;
   return check_launch(h, "k_cg_fused_hex8");
 }
@@ -1417,6 +1431,7 @@ int topopt_create(const topopt_desc* d, topopt_handle** out) {
   }
   if (const char* e = getenv("TOPOPT_CG_VARIANT")) h->cg_variant_env = atoi(e);
   if (const char* e = getenv("TOPOPT_CG_PERSIST")) h->cg_persist = atoi(e);
+  if (const char* e = getenv("TOPOPT_CG_FUSED_PDL")) h->cg_fused_pdl = atoi(e);
 
   // slab partition along the last axis
   const int NLg = (int)(h->dim == 3 ? gd.nz : gd.ny);

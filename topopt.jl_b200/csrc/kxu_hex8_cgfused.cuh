@@ -95,19 +95,6 @@ __global__ void __launch_bounds__(32 * (TYT + kFusedProducers), 1)
   __shared__ int sflag[TYT], cflag[TYT];
   __shared__ double zero3[4];
   __shared__ double sm[32];
-  if (st->done) return;
-  const int parity = st->iters & 1;
-#ifdef TOPOPT_TIMELINE
-  const int tl_slot = st->iters - 300;
-#endif
-  const double alpha = st->alpha, beta = st->beta;
-  const double* __restrict__ pin = vec.p[parity];
-  const double* __restrict__ rin = vec.r[parity];
-  const double* __restrict__ apin = vec.ap[parity];
-  double* __restrict__ pout = vec.p[parity ^ 1];
-  double* __restrict__ rout = vec.r[parity ^ 1];
-  double* __restrict__ y = vec.ap[parity ^ 1];
-  double* __restrict__ xsol = vec.x;
   const int tid = threadIdx.x;
   const int tx = tid & 31, wid = tid >> 5;
   const bool producer = wid >= TYT;
@@ -126,6 +113,22 @@ __global__ void __launch_bounds__(32 * (TYT + kFusedProducers), 1)
   for (int i = tid; i < 2 * 6 * (TYT + 1) * 32; i += (int)blockDim.x) (&yb[0][0][0][0])[i] = 0.0;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
+  // Programmatic dependent launch: everything above (220 KB of shared memory zeroed, barriers initialised) ran while the
+  // previous iteration's kernel was still finishing its reduction / all-reduce; nothing it wrote has been read yet.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (st->done) return;
+  const int parity = st->iters & 1;
+#ifdef TOPOPT_TIMELINE
+  const int tl_slot = st->iters - 300;
+#endif
+  const double alpha = st->alpha, beta = st->beta;
+  const double* __restrict__ pin = vec.p[parity];
+  const double* __restrict__ rin = vec.r[parity];
+  const double* __restrict__ apin = vec.ap[parity];
+  double* __restrict__ pout = vec.p[parity ^ 1];
+  double* __restrict__ rout = vec.r[parity ^ 1];
+  double* __restrict__ y = vec.ap[parity ^ 1];
+  double* __restrict__ xsol = vec.x;
 
   double dots[3] = {0.0, 0.0, 0.0};  // p.Ap, Ap.Ap, r.r
   const long long units = (long long)tilesX * tilesY * g.nown;
@@ -640,6 +643,7 @@ __global__ void __launch_bounds__(32 * (TYT + kFusedProducers), 1)
     }
   }
   if (tid == 0) TL_STAMP(2);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next iteration's CTAs may start their prologue
   block_partials_finish<3>(dots, partials, st, fin, sm, PEER);
   if (tid == 0) TL_STAMP(3);
 }
