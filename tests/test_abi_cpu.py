@@ -271,3 +271,33 @@ def test_save_mesh_vtu_like_the_reference(tmp_path):
     assert np.array_equal(disp.reshape(-1, 3), u[prob.metadata.node_dofs.T - 1])
     with pytest.raises(ValueError):
         t.save_mesh(str(tmp_path / "bad"), prob, rho[:-1])
+
+
+def test_struct_layouts_match_the_ctypes_and_julia_mirrors(tmp_path):
+    """The ABI structs are mirrored field by field in topopt.jl_b200/_lib.py (ctypes) and julia/TopOptCUDA.jl: sizes and
+    the offsets of the fields added this round must agree with what a C compiler lays out for include/topopt_cuda.h."""
+    import ctypes as C
+    import re
+    import subprocess
+
+    import topopt_jl_b200 as t
+
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stddef.h>\n#include <stdio.h>\n#include "topopt_cuda.h"\n'
+        'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(topopt_cg_opts), offsetof(topopt_cg_opts, variant), '
+        'offsetof(topopt_cg_opts, mg_degree), offsetof(topopt_cg_opts, mg_ratio), sizeof(topopt_cg_result), sizeof(topopt_stats), '
+        'sizeof(topopt_desc)); return 0; }\n'
+    )
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    L = t._lib
+    want = [C.sizeof(L.CGOpts), L.CGOpts.variant.offset, L.CGOpts.mg_degree.offset, L.CGOpts.mg_ratio.offset, C.sizeof(L.CGResult),
+            C.sizeof(L.Stats), C.sizeof(L.Desc)]
+    assert got == want, (got, want)
+    # the Julia mirror lists the same fields in the same order (isbits struct: same layout rules as C for these types)
+    jl = open(os.path.join(ROOT, "julia", "TopOptCUDA.jl")).read()
+    body = re.search(r"struct CGOpts.*?\nend", jl, re.S).group(0)
+    fields = re.findall(r"(\w+)::(?:Float64|Int32)", body)
+    assert fields == [name for name, _ in L.CGOpts._fields_], fields
